@@ -1,0 +1,1175 @@
+// lp_api.cu -- the C ABI of include/lpb200.h: context, data loading, host drivers of the kernels
+// (fitMuDisp, fitPi, evalLogLikMatrix, fitModel's EM loop) and the LRT.  No CPU fallback: every
+// compute entry point needs a CUDA device and fails with LPB200_E_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lp_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct lpb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // counts
+    int G = 0, N = 0;
+    bool is_u16 = false;
+    void *d_counts = nullptr;  // uint16_t or int32_t, gene-major
+    size_t pitch = 0;
+    int32_t *d_xmax = nullptr;
+    std::vector<double> row_means;
+    int global_max = 0;
+    // design
+    bool have_design = false;
+    DevDesign D{};
+    std::vector<void *> design_allocs;
+    std::vector<double> h_t;
+    double *d_Q = nullptr;        // orthonormal basis of impulse_basis, N x 4
+    bool have_starts = false;
+    std::vector<double> h_peak, h_valley;  // G x 7 column-major
+    std::vector<double> h_bs_mu;           // host copy of the mu spline basis (for Pinv)
+    // collective
+    int rank = 0, world = 1;
+    lpb200_allreduce_fn allreduce = nullptr;
+    void *allreduce_user = nullptr;
+    double *d_xchg = nullptr;  // small exchange buffer
+    // stats
+    lpb200_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int use_table = 1;
+};
+
+static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return set_err(ctx, LPB200_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {  // RAII device buffer
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+extern "C" int lpb200_abi_version(void) { return LPB200_ABI_VERSION; }
+
+extern "C" void lpb200_default_control(lpb200_control *c) {
+    c->maxit_mudisp = 1000;
+    c->reltol_mudisp = 1e-8;
+    c->maxit_pi = 10000;
+    c->reltol_pi = 1e-8;
+    c->ndeps = 1e-3;
+    c->max_cycles = 20;
+    c->prec_em = 1.0 - 1e-4;
+}
+
+extern "C" int lpb200_n_mu_params(const lpb200_model *m, const lpb200_design *d) {
+    return lp_n_mu_params(m->mu_model, d->k_spline_mu, d->n_groups);
+}
+extern "C" int lpb200_n_disp_params(const lpb200_model *m, const lpb200_design *d) {
+    return lp_n_disp_params(m->disp_model, d->k_spline_disp, d->n_groups);
+}
+extern "C" int lpb200_n_drop_params(const lpb200_model *m, const lpb200_design *d) {
+    if (m->drop_model == LPB200_DROP_NONE) return 0;
+    return 1 + (m->drop_model == LPB200_DROP_LOGISTIC_OFMU ? 1 : 0) + d->n_pi_pred;
+}
+extern "C" int lpb200_n_batch_cols(const int32_t *nb, int n_conf) {
+    int s = 0;
+    for (int c = 0; c < n_conf; c++) s += nb[c];
+    return s;
+}
+extern "C" int lpb200_deg_freedom(const lpb200_model *m, const lpb200_design *d) {
+    return lpb200_n_mu_params(m, d) + lpb200_n_batch_cols(d->n_batches_mu, d->n_conf_mu) - d->n_conf_mu +
+           lpb200_n_disp_params(m, d) + lpb200_n_batch_cols(d->n_batches_disp, d->n_conf_disp) - d->n_conf_disp;
+}
+
+extern "C" lpb200_ctx *lpb200_create(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    lpb200_ctx *c = new lpb200_ctx();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaMalloc((void **)&c->d_xchg, 64 * sizeof(double)) != cudaSuccess) {
+        delete c;
+        return nullptr;
+    }
+    const char *e = getenv("LPB200_NO_TABLE");
+    if (e && atoi(e)) c->use_table = 0;
+    return c;
+}
+
+static void free_design(lpb200_ctx *c) {
+    for (void *p : c->design_allocs) cudaFree(p);
+    c->design_allocs.clear();
+    c->d_Q = nullptr;
+    c->have_design = false;
+    c->have_starts = false;
+}
+
+extern "C" void lpb200_destroy(lpb200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_design(c);
+    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->d_xmax) cudaFree(c->d_xmax);
+    if (c->d_xchg) cudaFree(c->d_xchg);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+extern "C" const char *lpb200_last_error(lpb200_ctx *c) { return c ? c->err.c_str() : "no context (CUDA device unavailable)"; }
+
+extern "C" int lpb200_set_stream(lpb200_ctx *ctx, void *s) {
+    if (!ctx) return LPB200_E_ARG;
+    ctx->stream = (cudaStream_t)s;
+    return 0;
+}
+
+extern "C" int lpb200_set_collective(lpb200_ctx *ctx, int rank, int world, lpb200_allreduce_fn fn, void *user) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return set_err(ctx, LPB200_E_ARG, "bad collective");
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->allreduce = fn;
+    ctx->allreduce_user = user;
+    return 0;
+}
+
+extern "C" int lpb200_get_stats(lpb200_ctx *ctx, lpb200_stats *s) {
+    if (!ctx || !s) return LPB200_E_ARG;
+    *s = ctx->stats;
+    return 0;
+}
+extern "C" int lpb200_reset_stats(lpb200_ctx *ctx) {
+    if (!ctx) return LPB200_E_ARG;
+    ctx->stats = lpb200_stats{};
+    return 0;
+}
+
+static int do_allreduce(lpb200_ctx *ctx, double *dev, size_t count) {
+    if (ctx->world <= 1) return 0;
+    int rc = ctx->allreduce(ctx->allreduce_user, dev, count, (void *)ctx->stream);
+    if (rc != 0) return set_err(ctx, LPB200_E_COMM, "all-reduce callback failed (%d)", rc);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// data
+// ---------------------------------------------------------------------------------------------
+static int finish_counts(lpb200_ctx *ctx, int32_t *d_i32, int G, int N, size_t pitch) {
+    // row statistics, then narrow to uint16 when every count fits
+    DevBuf<double> d_mean;
+    CK(d_mean.alloc(G));
+    if (ctx->d_xmax) cudaFree(ctx->d_xmax);
+    CK(cudaMalloc((void **)&ctx->d_xmax, sizeof(int32_t) * G));
+    row_stats_kernel<<<G, 256, 0, ctx->stream>>>(d_i32, G, N, pitch, d_mean.p, ctx->d_xmax);
+    CK(cudaGetLastError());
+    ctx->row_means.resize(G);
+    std::vector<int32_t> xmax(G);
+    CK(cudaMemcpyAsync(ctx->row_means.data(), d_mean.p, sizeof(double) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(xmax.data(), ctx->d_xmax, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->global_max = 0;
+    for (int v : xmax) ctx->global_max = std::max(ctx->global_max, v);
+    if (ctx->d_counts) { cudaFree(ctx->d_counts); ctx->d_counts = nullptr; }
+    ctx->G = G;
+    ctx->N = N;
+    ctx->pitch = pitch;
+    if (ctx->global_max < (int)LP_NA_U16) {
+        uint16_t *d16 = nullptr;
+        CK(cudaMalloc((void **)&d16, sizeof(uint16_t) * (size_t)G * pitch));
+        narrow_u16_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_i32, d16, (size_t)G * pitch);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_i32);
+        ctx->d_counts = d16;
+        ctx->is_u16 = true;
+    } else {
+        ctx->d_counts = d_i32;
+        ctx->is_u16 = false;
+    }
+    ctx->stats.launches += 2;
+    ctx->have_starts = false;
+    return 0;
+}
+
+static size_t row_pitch(int N) { return ((size_t)N + 63) / 64 * 64; }
+
+extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const double *x) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (G <= 0 || N <= 0 || !x) return set_err(ctx, LPB200_E_ARG, "load_counts_dense: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    size_t pitch = row_pitch(N);
+    int32_t *d_i32 = nullptr;
+    CK(cudaMalloc((void **)&d_i32, sizeof(int32_t) * (size_t)G * pitch));
+    CK(cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * (size_t)G * pitch, ctx->stream));
+    // column slabs of the R matrix are contiguous: stream them through a bounded staging buffer
+    size_t slab_cols = std::max<size_t>(1, std::min<size_t>(N, ((size_t)256 << 20) / (sizeof(double) * (size_t)G)));
+    DevBuf<double> d_slab;
+    CK(d_slab.alloc(slab_cols * G));
+    for (size_t j0 = 0; j0 < (size_t)N; j0 += slab_cols) {
+        size_t nj = std::min(slab_cols, (size_t)N - j0);
+        CK(cudaMemcpyAsync(d_slab.p, x + j0 * G, sizeof(double) * nj * G, cudaMemcpyHostToDevice, ctx->stream));
+        dim3 grid((G + 31) / 32, (unsigned)((nj + 31) / 32)), block(32, 8);
+        pack_dense_kernel<<<grid, block, 0, ctx->stream>>>(d_slab.p, G, (int)j0, (int)nj, d_i32, pitch);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+    }
+    return finish_counts(ctx, d_i32, G, N, pitch);
+}
+
+extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32_t *p, const int32_t *i, const double *x) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (G <= 0 || N <= 0 || !p) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    size_t nnz = (size_t)p[N];
+    size_t pitch = row_pitch(N);
+    int32_t *d_i32 = nullptr;
+    CK(cudaMalloc((void **)&d_i32, sizeof(int32_t) * (size_t)G * pitch));
+    CK(cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * (size_t)G * pitch, ctx->stream));
+    DevBuf<int32_t> dp, di;
+    DevBuf<double> dx;
+    CK(dp.alloc(N + 1));
+    CK(di.alloc(nnz));
+    CK(dx.alloc(nnz));
+    CK(cudaMemcpyAsync(dp.p, p, sizeof(int32_t) * (N + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        CK(cudaMemcpyAsync(di.p, i, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dx.p, x, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    scatter_csc_kernel<<<N, 128, 0, ctx->stream>>>(dp.p, di.p, dx.p, N, d_i32, pitch);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return finish_counts(ctx, d_i32, G, N, pitch);
+}
+
+extern "C" int lpb200_load_counts_i32(lpb200_ctx *ctx, int G, int N, const int32_t *x, int is_device) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (G <= 0 || N <= 0 || !x) return set_err(ctx, LPB200_E_ARG, "load_counts_i32: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    size_t pitch = row_pitch(N);
+    int32_t *d_i32 = nullptr;
+    CK(cudaMalloc((void **)&d_i32, sizeof(int32_t) * (size_t)G * pitch));
+    CK(cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * (size_t)G * pitch, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_i32, pitch * sizeof(int32_t), x, (size_t)N * sizeof(int32_t), (size_t)N * sizeof(int32_t), G,
+                         is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    return finish_counts(ctx, d_i32, G, N, pitch);
+}
+
+extern "C" int lpb200_row_means(lpb200_ctx *ctx, double *means) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "counts not loaded");
+    memcpy(means, ctx->row_means.data(), sizeof(double) * ctx->G);
+    return 0;
+}
+
+// thin QR of an n x k column-major matrix by twice-iterated Gram-Schmidt (long double dots)
+static bool thin_qr(const double *B, int n, int k, std::vector<double> &Q, std::vector<double> &R) {
+    Q.assign(B, B + (size_t)n * k);
+    R.assign((size_t)k * k, 0.0);
+    for (int c = 0; c < k; c++) {
+        double *q = Q.data() + (size_t)c * n;
+        for (int pass = 0; pass < 2; pass++)
+            for (int p = 0; p < c; p++) {
+                const double *qp = Q.data() + (size_t)p * n;
+                long double dot = 0.0L;
+                for (int r = 0; r < n; r++) dot += (long double)qp[r] * q[r];
+                for (int r = 0; r < n; r++) q[r] -= (double)dot * qp[r];
+                R[p + (size_t)c * k] += (double)dot;
+            }
+        long double nrm = 0.0L;
+        for (int r = 0; r < n; r++) nrm += (long double)q[r] * q[r];
+        double nr = (double)sqrtl(nrm);
+        if (!(nr > 0)) return false;
+        R[c + (size_t)c * k] = nr;
+        for (int r = 0; r < n; r++) q[r] /= nr;
+    }
+    return true;
+}
+
+template <typename T>
+static int upload(lpb200_ctx *ctx, const T *h, size_t n, const T **d_out) {
+    T *d = nullptr;
+    CK(cudaMalloc((void **)&d, std::max<size_t>(n, 1) * sizeof(T)));
+    ctx->design_allocs.push_back(d);
+    CK(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = d;
+    return 0;
+}
+
+extern "C" int lpb200_set_design(lpb200_ctx *ctx, const lpb200_design *d) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (!d) return set_err(ctx, LPB200_E_ARG, "design is NULL");
+    if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "load counts before the design");
+    if (d->n_genes != ctx->G || d->n_cells != ctx->N)
+        return set_err(ctx, LPB200_E_ARG, "design is %d x %d but counts are %d x %d", d->n_genes, d->n_cells, ctx->G, ctx->N);
+    if (d->n_conf_mu > LPB200_MAX_CONF || d->n_conf_disp > LPB200_MAX_CONF || d->n_pi_pred > LPB200_MAX_PI_PRED ||
+        d->n_conf_mu < 0 || d->n_conf_disp < 0 || d->n_pi_pred < 0)
+        return set_err(ctx, LPB200_E_ARG, "too many confounders / drop-out predictors");
+    CK(cudaSetDevice(ctx->device));
+    free_design(ctx);
+    DevDesign &D = ctx->D;
+    D = DevDesign{};
+    const int G = ctx->G, N = ctx->N;
+    D.G = G;
+    D.N = N;
+    int rc;
+    if (d->size_factors) {
+        bool all_one = true;
+        for (int j = 0; j < N; j++)
+            if (d->size_factors[j] != 1.0) { all_one = false; break; }
+        if (!all_one && (rc = upload(ctx, d->size_factors, N, &D.sf))) return rc;
+    }
+    ctx->h_t.clear();
+    if (d->pseudotime) {
+        if ((rc = upload(ctx, d->pseudotime, N, &D.t))) return rc;
+        ctx->h_t.assign(d->pseudotime, d->pseudotime + N);
+    }
+    if (d->group_idx) {
+        for (int j = 0; j < N; j++)
+            if (d->group_idx[j] < 0 || d->group_idx[j] >= d->n_groups) return set_err(ctx, LPB200_E_ARG, "group index out of range");
+        if ((rc = upload(ctx, d->group_idx, N, &D.group))) return rc;
+        D.n_groups = d->n_groups;
+    }
+    ctx->h_bs_mu.clear();
+    if (d->spline_basis_mu && d->k_spline_mu > 0) {
+        if ((rc = upload(ctx, d->spline_basis_mu, (size_t)N * d->k_spline_mu, &D.bs_mu))) return rc;
+        D.k_mu = d->k_spline_mu;
+        ctx->h_bs_mu.assign(d->spline_basis_mu, d->spline_basis_mu + (size_t)N * d->k_spline_mu);
+    }
+    if (d->spline_basis_disp && d->k_spline_disp > 0) {
+        if ((rc = upload(ctx, d->spline_basis_disp, (size_t)N * d->k_spline_disp, &D.bs_disp))) return rc;
+        D.k_disp = d->k_spline_disp;
+    }
+    D.n_conf_mu = d->n_conf_mu;
+    if (d->n_conf_mu > 0) {
+        for (int c = 0; c < d->n_conf_mu; c++) {
+            D.nb_mu[c] = d->n_batches_mu[c];
+            for (int j = 0; j < N; j++) {
+                int b = d->batch_idx_mu[(size_t)c * N + j];
+                if (b < 0 || b >= D.nb_mu[c]) return set_err(ctx, LPB200_E_ARG, "mu batch index out of range");
+            }
+        }
+        if ((rc = upload(ctx, d->batch_idx_mu, (size_t)N * d->n_conf_mu, &D.bidx_mu))) return rc;
+    }
+    D.n_conf_disp = d->n_conf_disp;
+    if (d->n_conf_disp > 0) {
+        for (int c = 0; c < d->n_conf_disp; c++) {
+            D.nb_disp[c] = d->n_batches_disp[c];
+            for (int j = 0; j < N; j++) {
+                int b = d->batch_idx_disp[(size_t)c * N + j];
+                if (b < 0 || b >= D.nb_disp[c]) return set_err(ctx, LPB200_E_ARG, "dispersion batch index out of range");
+            }
+        }
+        if ((rc = upload(ctx, d->batch_idx_disp, (size_t)N * d->n_conf_disp, &D.bidx_disp))) return rc;
+    }
+    if (d->pi_const_pred && d->n_pi_pred > 0) {
+        if ((rc = upload(ctx, d->pi_const_pred, (size_t)G * d->n_pi_pred, &D.pi_pred))) return rc;
+        D.P = d->n_pi_pred;
+    }
+    if (d->impulse_basis) {
+        std::vector<double> Q, R;
+        if (!thin_qr(d->impulse_basis, N, 4, Q, R)) return set_err(ctx, LPB200_E_ARG, "impulse_basis is rank deficient");
+        const double *dq = nullptr;
+        if ((rc = upload(ctx, Q.data(), (size_t)N * 4, &dq))) return rc;
+        ctx->d_Q = const_cast<double *>(dq);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_design = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// model bookkeeping
+// ---------------------------------------------------------------------------------------------
+static int make_model(lpb200_ctx *ctx, const lpb200_model *m, DevModel &M) {
+    const DevDesign &D = ctx->D;
+    if (m->mu_model == LPB200_MU_MM)  // fitMeanDispersion.R:804, evalLogLik.R:271: stop("... not yet supported")
+        return set_err(ctx, LPB200_E_NOTSUP, "LineagePulse ERROR: strMuModel=\"MM\" not yet supported (reference stub)");
+    M = DevModel{};
+    M.mu_model = m->mu_model;
+    M.disp_model = m->disp_model;
+    M.drop_model = m->drop_model;
+    M.p_mu = lp_n_mu_params(m->mu_model, D.k_mu, D.n_groups);
+    M.p_disp = lp_n_disp_params(m->disp_model, D.k_disp, D.n_groups);
+    if (M.p_mu <= 0 || M.p_disp <= 0) return set_err(ctx, LPB200_E_ARG, "model needs covariates the design does not have");
+    if (m->drop_model != LPB200_DROP_NONE && m->drop_model != LPB200_DROP_LOGISTIC && m->drop_model != LPB200_DROP_LOGISTIC_OFMU)
+        return set_err(ctx, LPB200_E_ARG, "unknown drop-out model %d", m->drop_model);
+    if (m->mu_model == LPB200_MU_IMPULSE && !D.t) return set_err(ctx, LPB200_E_ARG, "impulse model needs pseudotime");
+    M.q_drop = m->drop_model == LPB200_DROP_NONE ? 0 : 1 + (m->drop_model == LPB200_DROP_LOGISTIC_OFMU ? 1 : 0) + D.P;
+    for (int c = 0; c < D.n_conf_mu; c++) M.nbf_mu += D.nb_mu[c];
+    for (int c = 0; c < D.n_conf_disp; c++) M.nbf_disp += D.nb_disp[c];
+    M.n_theta = M.p_disp + (M.nbf_disp - D.n_conf_disp) + M.p_mu + (M.nbf_mu - D.n_conf_mu);
+    if (M.n_theta > LPB200_MAX_PARAMS || M.p_mu > LP_MAX_PMU || M.p_disp > LP_MAX_PDISP || M.nbf_mu > LP_MAX_BMU ||
+        M.nbf_disp > LP_MAX_BDISP || M.q_drop > LP_PI_NP)
+        return set_err(ctx, LPB200_E_ARG, "model too large: n_theta=%d p_mu=%d p_disp=%d batch=%d/%d q=%d", M.n_theta, M.p_mu,
+                       M.p_disp, M.nbf_mu, M.nbf_disp, M.q_drop);
+    return 0;
+}
+
+static int require_ready(lpb200_ctx *ctx) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "counts not loaded");
+    if (!ctx->have_design) return set_err(ctx, LPB200_E_STATE, "design not set");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return set_err(ctx, LPB200_E_CUDA, "cudaSetDevice failed");
+    return 0;
+}
+
+// R matrices (column-major) <-> nat vectors [G][n_nat]
+static void params_to_nat(const lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p, std::vector<double> &nat) {
+    const DevDesign &D = ctx->D;
+    const int G = ctx->G, n_nat = lp_n_nat(M);
+    nat.resize((size_t)G * n_nat);
+    for (int i = 0; i < G; i++) {
+        double *v = nat.data() + (size_t)i * n_nat;
+        int u = 0;
+        for (int k = 0; k < M.p_disp; k++) v[u++] = p->mat_disp[i + (size_t)k * G];
+        size_t off = 0;
+        for (int c = 0; c < D.n_conf_disp; c++) {
+            for (int b = 0; b < D.nb_disp[c]; b++) v[u++] = p->batch_disp[off + i + (size_t)b * G];
+            off += (size_t)G * D.nb_disp[c];
+        }
+        for (int k = 0; k < M.p_mu; k++) v[u++] = p->mat_mu[i + (size_t)k * G];
+        off = 0;
+        for (int c = 0; c < D.n_conf_mu; c++) {
+            for (int b = 0; b < D.nb_mu[c]; b++) v[u++] = p->batch_mu[off + i + (size_t)b * G];
+            off += (size_t)G * D.nb_mu[c];
+        }
+    }
+}
+
+static void nat_to_params(const lpb200_ctx *ctx, const DevModel &M, const double *v, int i, lpb200_params *p) {
+    const DevDesign &D = ctx->D;
+    const int G = ctx->G;
+    int u = 0;
+    for (int k = 0; k < M.p_disp; k++) p->mat_disp[i + (size_t)k * G] = v[u++];
+    size_t off = 0;
+    for (int c = 0; c < D.n_conf_disp; c++) {
+        for (int b = 0; b < D.nb_disp[c]; b++) p->batch_disp[off + i + (size_t)b * G] = v[u++];
+        off += (size_t)G * D.nb_disp[c];
+    }
+    for (int k = 0; k < M.p_mu; k++) p->mat_mu[i + (size_t)k * G] = v[u++];
+    off = 0;
+    for (int c = 0; c < D.n_conf_mu; c++) {
+        for (int b = 0; b < D.nb_mu[c]; b++) p->batch_mu[off + i + (size_t)b * G] = v[u++];
+        off += (size_t)G * D.nb_mu[c];
+    }
+}
+
+static CountView count_view(const lpb200_ctx *ctx) {
+    CountView C;
+    C.ptr = ctx->d_counts;
+    C.pitch = ctx->pitch;
+    C.xmax = ctx->d_xmax;
+    return C;
+}
+
+static int fit_threads(int N) { return N >= 2048 ? 256 : 128; }
+
+// drop-out inputs shared by the fit / eval kernels
+struct DropBufs {
+    DevBuf<double> drop, pi, l1m, pi_scr, l1m_scr;
+};
+static int setup_drop(lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p, int grid, FitArgs &A, DropBufs &B) {
+    const int N = ctx->N;
+    A.drop = nullptr;
+    A.pi_glob = A.l1m_glob = nullptr;
+    A.pi_scratch = A.l1m_scratch = nullptr;
+    if (M.drop_model == LPB200_DROP_NONE) return 0;
+    if (!p->mat_drop) return set_err(ctx, LPB200_E_ARG, "mat_drop is NULL but the drop-out model is not \"none\"");
+    CK(B.drop.alloc((size_t)N * M.q_drop));
+    CK(cudaMemcpyAsync(B.drop.p, p->mat_drop, sizeof(double) * (size_t)N * M.q_drop, cudaMemcpyHostToDevice, ctx->stream));
+    A.drop = B.drop.p;
+    if (M.drop_model == LPB200_DROP_LOGISTIC) {
+        if (ctx->D.P == 0) {
+            CK(B.pi.alloc(N));
+            CK(B.l1m.alloc(N));
+            pi_vector_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->D, M, B.drop.p, B.pi.p, B.l1m.p);
+            CK(cudaGetLastError());
+            ctx->stats.launches++;
+            A.pi_glob = B.pi.p;
+            A.l1m_glob = B.l1m.p;
+        } else {
+            CK(B.pi_scr.alloc((size_t)grid * N));
+            CK(B.l1m_scr.alloc((size_t)grid * N));
+            A.pi_scratch = B.pi_scr.p;
+            A.l1m_scratch = B.l1m_scr.p;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evalLogLikMatrix
+// ---------------------------------------------------------------------------------------------
+static int eval_loglik_impl(lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p, double *ll) {
+    const int G = ctx->G, N = ctx->N;
+    std::vector<double> nat;
+    params_to_nat(ctx, M, p, nat);
+    DevBuf<double> d_nat, d_ll;
+    CK(d_nat.alloc(nat.size()));
+    CK(d_ll.alloc(G));
+    CK(cudaMemcpyAsync(d_nat.p, nat.data(), sizeof(double) * nat.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = fit_threads(N);
+    const int grid = std::min(G, ctx->sm_count * 4);
+    FitArgs A{};
+    A.D = ctx->D;
+    A.M = M;
+    A.C = count_view(ctx);
+    A.theta0 = d_nat.p;
+    A.ll_out = d_ll.p;
+    A.use_table = ctx->use_table;
+    DropBufs B;
+    int rc = setup_drop(ctx, M, p, grid, A, B);
+    if (rc) return rc;
+    const size_t smem = sizeof(FitShared);
+    if (ctx->is_u16) {
+        CK(cudaFuncSetAttribute(eval_ll_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_ll_kernel<uint16_t><<<grid, threads, smem, ctx->stream>>>(A);
+    } else {
+        CK(cudaFuncSetAttribute(eval_ll_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_ll_kernel<int32_t><<<grid, threads, smem, ctx->stream>>>(A);
+    }
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    ctx->stats.fn_evals += (uint64_t)G;
+    ctx->stats.ole += (uint64_t)G * N;
+    CK(cudaMemcpyAsync(ll, d_ll.p, sizeof(double) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lpb200_eval_loglik(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, double *ll) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if ((rc = make_model(ctx, m, M))) return rc;
+    return eval_loglik_impl(ctx, M, p, ll);
+}
+
+// ---------------------------------------------------------------------------------------------
+// initialiseImpulseParameters (cached: depends only on the data)
+// ---------------------------------------------------------------------------------------------
+static int ensure_starts(lpb200_ctx *ctx) {
+    if (ctx->have_starts) return 0;
+    if (!ctx->d_Q || !ctx->D.t) return set_err(ctx, LPB200_E_ARG, "impulse starts need pseudotime and impulse_basis");
+    const int G = ctx->G, N = ctx->N;
+    const int grid = std::min(G, ctx->sm_count * 4);
+    DevBuf<double> d_peak, d_valley, d_fit;
+    CK(d_peak.alloc((size_t)G * 7));
+    CK(d_valley.alloc((size_t)G * 7));
+    CK(d_fit.alloc((size_t)grid * N));
+    StartsArgs A{};
+    A.D = ctx->D;
+    A.C = count_view(ctx);
+    A.Q = ctx->d_Q;
+    A.tmin = *std::min_element(ctx->h_t.begin(), ctx->h_t.end());
+    A.tmax = *std::max_element(ctx->h_t.begin(), ctx->h_t.end());
+    A.t_first = ctx->h_t.front();
+    A.t_last = ctx->h_t.back();
+    A.peak = d_peak.p;
+    A.valley = d_valley.p;
+    A.fit_scratch = d_fit.p;
+    if (ctx->is_u16) impulse_starts_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(A);
+    else impulse_starts_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(A);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    ctx->h_peak.resize((size_t)G * 7);
+    ctx->h_valley.resize((size_t)G * 7);
+    CK(cudaMemcpyAsync(ctx->h_peak.data(), d_peak.p, sizeof(double) * G * 7, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_valley.data(), d_valley.p, sizeof(double) * G * 7, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_starts = true;
+    return 0;
+}
+
+extern "C" int lpb200_impulse_starts(lpb200_ctx *ctx, double *peak, double *valley) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_starts(ctx))) return rc;
+    memcpy(peak, ctx->h_peak.data(), sizeof(double) * ctx->G * 7);
+    memcpy(valley, ctx->h_valley.data(), sizeof(double) * ctx->G * 7);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fitMuDisp
+// ---------------------------------------------------------------------------------------------
+static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p, const lpb200_control *c, double *ll,
+                           int32_t *conv) {
+    const DevDesign &D = ctx->D;
+    const int G = ctx->G, N = ctx->N, n = M.n_theta, n_nat = lp_n_nat(M);
+    const bool impulse = M.mu_model == LPB200_MU_IMPULSE;
+    const int n_starts = impulse ? 3 : 1;
+    int rc;
+    if (impulse && (rc = ensure_starts(ctx))) return rc;
+    std::vector<double> nat;
+    params_to_nat(ctx, M, p, nat);
+    // theta0 per (gene, start); impulse start order Peak, Valley, Prior (fitMeanDispersion.R:663)
+    const size_t n_items = (size_t)G * n_starts;
+    std::vector<double> theta0(n_items * n);
+    for (int i = 0; i < G; i++) {
+        PointNat g;
+        lp_nat_load(M, nat.data() + (size_t)i * n_nat, g);
+        if (impulse) {
+            double coords[3][7];
+            for (int k = 0; k < 7; k++) {
+                coords[0][k] = ctx->h_peak[i + (size_t)k * G];
+                coords[1][k] = ctx->h_valley[i + (size_t)k * G];
+                coords[2][k] = g.mu[k];
+            }
+            for (int k = 2; k < 5; k++) coords[2][k] = log(coords[2][k]);  // :621-622
+            for (int s = 0; s < 3; s++) lp_pack_theta(D, M, g, coords[s], theta0.data() + ((size_t)i * 3 + s) * n);
+        } else {
+            lp_pack_theta(D, M, g, nullptr, theta0.data() + (size_t)i * n);
+        }
+    }
+    DevBuf<double> d_theta0, d_theta_out, d_ll;
+    DevBuf<int> d_conv, d_queue;
+    DevBuf<unsigned> d_evals;
+    CK(d_theta0.alloc(theta0.size()));
+    CK(d_theta_out.alloc(theta0.size()));
+    CK(d_ll.alloc(n_items));
+    CK(d_conv.alloc(n_items));
+    CK(d_evals.alloc(n_items));
+    CK(d_queue.alloc(1));
+    CK(cudaMemcpyAsync(d_theta0.p, theta0.data(), sizeof(double) * theta0.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_queue.p, 0, sizeof(int), ctx->stream));
+    const int threads = fit_threads(N);
+    const int grid = (int)std::min<size_t>(n_items, (size_t)ctx->sm_count * 4);
+    FitArgs A{};
+    A.D = D;
+    A.M = M;
+    A.C = count_view(ctx);
+    A.n_items = (int)n_items;
+    A.n_starts = n_starts;
+    A.queue = d_queue.p;
+    A.theta0 = d_theta0.p;
+    A.maxit = c->maxit_mudisp;
+    A.reltol = c->reltol_mudisp;
+    A.ndeps = c->ndeps;
+    A.theta_out = d_theta_out.p;
+    A.ll_out = d_ll.p;
+    A.conv_out = d_conv.p;
+    A.evals_out = d_evals.p;
+    A.use_table = ctx->use_table;
+    DropBufs B;
+    if ((rc = setup_drop(ctx, M, p, grid, A, B))) return rc;
+    const size_t smem = sizeof(FitShared);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->is_u16) {
+        CK(cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_mudisp_kernel<uint16_t><<<grid, threads, smem, ctx->stream>>>(A);
+    } else {
+        CK(cudaFuncSetAttribute(fit_mudisp_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_mudisp_kernel<int32_t><<<grid, threads, smem, ctx->stream>>>(A);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->stats.launches++;
+    std::vector<double> theta_out(theta0.size()), ll_items(n_items);
+    std::vector<int> conv_items(n_items);
+    std::vector<unsigned> evals(n_items);
+    CK(cudaMemcpyAsync(theta_out.data(), d_theta_out.p, sizeof(double) * theta_out.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ll_items.data(), d_ll.p, sizeof(double) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(conv_items.data(), d_conv.p, sizeof(int) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(evals.data(), d_evals.p, sizeof(unsigned) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.kernel_ms += ms;
+    bool nonfinite = false;
+    for (int i = 0; i < G; i++) {
+        int best = 0;
+        bool any_bad = false;
+        for (int s = 0; s < n_starts; s++) {
+            size_t it = (size_t)i * n_starts + s;
+            ctx->stats.fn_evals += evals[it];
+            ctx->stats.ole += (uint64_t)evals[it] * N;
+            if (conv_items[it] == 1001 || std::isnan(ll_items[it])) any_bad = true;
+        }
+        if (any_bad) {  // optim() error => the reference aborts (fitMeanDispersion.R:384-389)
+            ll[i] = NAN;
+            conv[i] = 1001;
+            nonfinite = true;
+            continue;
+        }
+        for (int s = 1; s < n_starts; s++)  // first maximum in the order Peak, Valley, Prior (:664-671)
+            if (ll_items[(size_t)i * n_starts + s] > ll_items[(size_t)i * n_starts + best]) best = s;
+        size_t it = (size_t)i * n_starts + best;
+        PointNat g;
+        lp_unpack_theta(D, M, theta_out.data() + it * n, g);  // same clamps as :391-498
+        double v[LPB200_MAX_PARAMS * 3];
+        lp_nat_store(M, g, v);
+        nat_to_params(ctx, M, v, i, p);
+        ll[i] = ll_items[it];
+        conv[i] = conv_items[it];
+    }
+    if (nonfinite) return set_err(ctx, LPB200_E_NONFINITE, "fitMuDisp: non-finite objective (optim would have raised an error)");
+    return 0;
+}
+
+extern "C" int lpb200_fit_mudisp(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll,
+                                 int32_t *conv) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if ((rc = make_model(ctx, m, M))) return rc;
+    return fit_mudisp_impl(ctx, M, p, c, ll, conv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fitPi
+// ---------------------------------------------------------------------------------------------
+template <typename CT>
+static void launch_pi_eval(lpb200_ctx *ctx, const PiArgs &A) {
+    dim3 grid((ctx->N + 127) / 128, A.n_chunks);
+    pi_eval_kernel<CT><<<grid, 128, 0, ctx->stream>>>(A);
+}
+
+static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, lpb200_params *p, const lpb200_control *c,
+                       double *ll, int32_t *conv) {
+    const int G = ctx->G, N = ctx->N, q = M.q_drop;
+    if (M.drop_model == LPB200_DROP_NONE) return set_err(ctx, LPB200_E_ARG, "fitPi needs a drop-out model");
+    if (!p->mat_drop) return set_err(ctx, LPB200_E_ARG, "mat_drop is NULL");
+    std::vector<double> nat;
+    params_to_nat(ctx, M, p, nat);
+    DevBuf<double> d_nat, d_drop, d_partial, d_vals, d_ll, d_total;
+    DevBuf<PiState> d_states;
+    DevBuf<int> d_active, d_conv;
+    DevBuf<unsigned> d_evals;
+    const int cell_blocks = (N + 127) / 128;
+    int n_chunks = std::max(1, std::min(64, (ctx->sm_count * 4 + cell_blocks - 1) / cell_blocks));
+    n_chunks = std::min(n_chunks, G);
+    const int gpc = (G + n_chunks - 1) / n_chunks;
+    n_chunks = (G + gpc - 1) / gpc;
+    CK(d_nat.alloc(nat.size()));
+    CK(d_drop.alloc((size_t)N * q));
+    CK(d_partial.alloc((size_t)n_chunks * LP_PI_KP * N));
+    CK(d_vals.alloc((size_t)LP_PI_KP * N));
+    CK(d_states.alloc(N));
+    CK(d_active.alloc(1));
+    CK(d_total.alloc(LP_PI_KP));
+    CK(cudaMemcpyAsync(d_nat.p, nat.data(), sizeof(double) * nat.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_drop.p, p->mat_drop, sizeof(double) * (size_t)N * q, cudaMemcpyHostToDevice, ctx->stream));
+    PiArgs A{};
+    A.D = ctx->D;
+    A.M = M;
+    A.C = count_view(ctx);
+    A.nat = d_nat.p;
+    A.states = d_states.p;
+    A.partial = d_partial.p;
+    A.vals = d_vals.p;
+    A.genes_per_chunk = gpc;
+    A.n_chunks = n_chunks;
+    A.shared_nk = 0;
+    A.n_active = d_active.p;
+    A.ndeps = c->ndeps;
+    const int nb = (N + 127) / 128;
+    int rc;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+
+    if (drop_fit_group == LPB200_DROPFIT_PERCELL) {
+        pi_start_kernel<<<nb, 128, 0, ctx->stream>>>(A, d_drop.p, c->maxit_pi, c->reltol_pi);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+        for (long round = 0;; round++) {
+            CK(cudaMemsetAsync(d_active.p, 0, sizeof(int), ctx->stream));
+            if (ctx->is_u16) launch_pi_eval<uint16_t>(ctx, A);
+            else launch_pi_eval<int32_t>(ctx, A);
+            CK(cudaGetLastError());
+            pi_reduce_kernel<<<nb, 128, 0, ctx->stream>>>(A);
+            CK(cudaGetLastError());
+            if ((rc = do_allreduce(ctx, d_vals.p, (size_t)LP_PI_KP * N))) return rc;
+            pi_advance_kernel<<<nb, 128, 0, ctx->stream>>>(A);
+            CK(cudaGetLastError());
+            ctx->stats.launches += 3;
+            int active = 0;
+            CK(cudaMemcpyAsync(&active, d_active.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (active == 0) break;
+        }
+        CK(d_ll.alloc(N));
+        CK(d_conv.alloc(N));
+        CK(d_evals.alloc(N));
+        pi_finish_kernel<<<nb, 128, 0, ctx->stream>>>(A, d_drop.p, d_ll.p, d_conv.p, d_evals.p);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+        std::vector<unsigned> evals(N);
+        CK(cudaMemcpyAsync(p->mat_drop, d_drop.p, sizeof(double) * (size_t)N * q, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ll, d_ll.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(conv, d_conv.p, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(evals.data(), d_evals.p, sizeof(unsigned) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool nonfinite = false;
+        for (int j = 0; j < N; j++) {
+            ctx->stats.fn_evals += evals[j];
+            ctx->stats.ole += (uint64_t)evals[j] * G;
+            if (conv[j] == 1001) nonfinite = true;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->stats.kernel_ms += ms;
+        if (nonfinite) return set_err(ctx, LPB200_E_NONFINITE, "fitPi: non-finite objective (optim would have raised an error)");
+        return 0;
+    }
+
+    // ForAllCells (fitDropout.R:480-499): one theta, objective = sum over the whole matrix
+    PiState st;
+    double th0[LP_PI_NP];
+    for (int k = 0; k < q; k++) th0[k] = p->mat_drop[0 + (size_t)k * N];  // all rows are the same
+    if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) th0[1] = log(-th0[1]);
+    bfgs_start(st, q, th0, c->maxit_pi, c->reltol_pi, c->ndeps);
+    double vals[LP_PI_KP];
+    while (st.req != LP_REQ_NONE) {
+        int nk = (st.req == LP_REQ_F) ? 1 : 2 * q;
+        for (int k = 0; k < nk; k++) {
+            for (int i = 0; i < q; i++) A.shared_theta[k * LP_PI_NP + i] = st.b[i];
+            if (st.req == LP_REQ_GRAD) {
+                int cc = bfgs_grad_coord(k);
+                A.shared_theta[k * LP_PI_NP + cc] = bfgs_grad_point(st.b[cc], k, c->ndeps);
+            }
+        }
+        A.shared_nk = nk;
+        if (ctx->is_u16) launch_pi_eval<uint16_t>(ctx, A);
+        else launch_pi_eval<int32_t>(ctx, A);
+        CK(cudaGetLastError());
+        pi_reduce_kernel<<<nb, 128, 0, ctx->stream>>>(A);
+        CK(cudaGetLastError());
+        pi_total_kernel<<<nk, 256, 0, ctx->stream>>>(d_vals.p, N, d_total.p);
+        CK(cudaGetLastError());
+        ctx->stats.launches += 3;
+        if ((rc = do_allreduce(ctx, d_total.p, (size_t)nk))) return rc;
+        CK(cudaMemcpyAsync(vals, d_total.p, sizeof(double) * nk, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.fn_evals += (uint64_t)nk;
+        ctx->stats.ole += (uint64_t)nk * G * N;
+        bfgs_advance(st, vals);
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.kernel_ms += ms;
+    conv[0] = st.fail;
+    if (st.fail == 1001) {
+        ll[0] = NAN;
+        return set_err(ctx, LPB200_E_NONFINITE, "fitPi (ForAllCells): non-finite objective");
+    }
+    double lin[LP_PI_NP];
+    lp_pi_transform(M.drop_model, q, st.b, lin);
+    for (int k = 0; k < q; k++)
+        for (int j = 0; j < N; j++) p->mat_drop[j + (size_t)k * N] = lin[k];
+    ll[0] = -st.Fmin;
+    return 0;
+}
+
+extern "C" int lpb200_fit_pi(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll,
+                             int32_t *conv) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if ((rc = make_model(ctx, m, M))) return rc;
+    return fit_pi_impl(ctx, M, m->drop_fit_group, p, c, ll, conv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// initial values (initialiseMuModel.R:93-133, initialiseDispModel.R:89-130, initialiseDropModel.R:73-91)
+// ---------------------------------------------------------------------------------------------
+static int init_params_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *out, double min_rowmean_global, bool init_drop) {
+    const DevDesign &D = ctx->D;
+    const int G = ctx->G, N = ctx->N;
+    double minmean = INFINITY;
+    for (int i = 0; i < G; i++) minmean = std::min(minmean, ctx->row_means[i]);
+    if (!std::isnan(min_rowmean_global)) minmean = min_rowmean_global;
+    for (int i = 0; i < G; i++) {
+        double mi = ctx->row_means[i];
+        if (mi < 1e-10) mi = 1e-10;
+        if (M.mu_model == LPB200_MU_CONSTANT) out->mat_mu[i] = mi;
+        else if (M.mu_model == LPB200_MU_IMPULSE) {
+            for (int k = 0; k < 7; k++) out->mat_mu[i + (size_t)k * G] = (k >= 2 && k < 5) ? mi : 1.0;
+        } else if (M.mu_model == LPB200_MU_GROUPS) {
+            for (int k = 0; k < M.p_mu; k++) out->mat_mu[i + (size_t)k * G] = mi;
+        }
+        for (int k = 0; k < M.p_disp; k++)
+            out->mat_disp[i + (size_t)k * G] = (M.disp_model == LPB200_DISP_SPLINES && k > 0) ? 0.0 : 1.0;
+    }
+    if (M.mu_model == LPB200_MU_SPLINES) {  // lm(log(x+1) ~ 0 + basis)$coef = R^-1 Q^T y
+        const int K = M.p_mu;
+        std::vector<double> Q, R;
+        if (!thin_qr(ctx->h_bs_mu.data(), N, K, Q, R)) return set_err(ctx, LPB200_E_ARG, "spline basis is rank deficient");
+        std::vector<double> Pinv((size_t)K * N);  // row-major K x N
+        for (int j = 0; j < N; j++) {
+            double col[LP_MAX_PMU];
+            for (int cidx = K - 1; cidx >= 0; cidx--) {
+                double s = Q[j + (size_t)cidx * N];
+                for (int pp = cidx + 1; pp < K; pp++) s -= R[cidx + (size_t)pp * K] * col[pp];
+                col[cidx] = s / R[cidx + (size_t)cidx * K];
+            }
+            for (int k = 0; k < K; k++) Pinv[(size_t)k * N + j] = col[k];
+        }
+        DevBuf<double> d_pinv, d_coef;
+        CK(d_pinv.alloc(Pinv.size()));
+        CK(d_coef.alloc((size_t)G * K));
+        CK(cudaMemcpyAsync(d_pinv.p, Pinv.data(), sizeof(double) * Pinv.size(), cudaMemcpyHostToDevice, ctx->stream));
+        const int grid = std::min(G, ctx->sm_count * 8);
+        if (ctx->is_u16) spline_init_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(D, count_view(ctx), d_pinv.p, K, d_coef.p);
+        else spline_init_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(D, count_view(ctx), d_pinv.p, K, d_coef.p);
+        CK(cudaGetLastError());
+        ctx->stats.launches++;
+        CK(cudaMemcpyAsync(out->mat_mu, d_coef.p, sizeof(double) * (size_t)G * K, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (D.n_conf_mu > 0) {
+        if (!out->batch_mu) return set_err(ctx, LPB200_E_ARG, "batch_mu is NULL");
+        for (size_t k = 0; k < (size_t)G * M.nbf_mu; k++) out->batch_mu[k] = 1.0;
+    }
+    if (D.n_conf_disp > 0) {
+        if (!out->batch_disp) return set_err(ctx, LPB200_E_ARG, "batch_disp is NULL");
+        for (size_t k = 0; k < (size_t)G * M.nbf_disp; k++) out->batch_disp[k] = 1.0;
+    }
+    if (init_drop && M.drop_model != LPB200_DROP_NONE && out->mat_drop) {
+        const double target = 0.99;
+        for (int k = 0; k < M.q_drop; k++)
+            for (int j = 0; j < N; j++) out->mat_drop[j + (size_t)k * N] = 0.0;
+        if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) {
+            const double slope = -1.0;
+            const double off = log(target) - log(1 - target) - slope * log(minmean);
+            for (int j = 0; j < N; j++) {
+                out->mat_drop[j] = off;
+                out->mat_drop[j + (size_t)N] = slope;
+            }
+        } else {
+            const double off = log(target) - log(1 - target);
+            for (int j = 0; j < N; j++) out->mat_drop[j] = off;
+        }
+    }
+    return 0;
+}
+
+extern "C" int lpb200_init_params(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *out, double min_rowmean_global) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if ((rc = make_model(ctx, m, M))) return rc;
+    return init_params_impl(ctx, M, out, min_rowmean_global, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fitModel: the EM / coordinate-ascent loop (fitModel.R:137-356)
+// ---------------------------------------------------------------------------------------------
+static int sum_ll(lpb200_ctx *ctx, const double *ll, int G, double *out) {
+    long double s = 0.0L;
+    for (int i = 0; i < G; i++) s += ll[i];
+    double v = (double)s;
+    if (ctx->world > 1) {  // sum over the gene shards
+        CK(cudaMemcpyAsync(ctx->d_xchg, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = do_allreduce(ctx, ctx->d_xchg, 1);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&v, ctx->d_xchg, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = v;
+    return 0;
+}
+
+extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop,
+                                const lpb200_control *c, double min_rowmean_global, double *em_ll, int32_t *n_iter,
+                                int32_t *converged, double *ll_init, double *ll, int32_t *conv) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if ((rc = make_model(ctx, m, M))) return rc;
+    const int G = ctx->G, N = ctx->N;
+    if (fit_drop && M.drop_model == LPB200_DROP_NONE) fit_drop = 0;
+    const int max_cycles = fit_drop ? c->max_cycles : 1;  // fitModel.R:181-183
+    for (int k = 0; k < max_cycles; k++) em_ll[k] = NAN;
+    if ((rc = init_params_impl(ctx, M, p, min_rowmean_global, fit_drop != 0))) return rc;
+    if ((rc = eval_loglik_impl(ctx, M, p, ll))) return rc;  // :228-233
+    double ll_new, ll_old = NAN;
+    if ((rc = sum_ll(ctx, ll, G, &ll_new))) return rc;
+    if (ll_init) *ll_init = ll_new;
+    int iter = 1;
+    std::vector<double> pill(fit_drop ? N : 1);
+    std::vector<int32_t> piconv(fit_drop ? N : 1);
+    int any_nonconv = 0;
+    while (iter == 1 || (ll_new > ll_old * c->prec_em && iter <= max_cycles)) {  // :242-243
+        if (fit_drop && (rc = fit_pi_impl(ctx, M, m->drop_fit_group, p, c, pill.data(), piconv.data()))) return rc;
+        if ((rc = fit_mudisp_impl(ctx, M, p, c, ll, conv))) return rc;
+        ll_old = ll_new;
+        if ((rc = sum_ll(ctx, ll, G, &ll_new))) return rc;
+        em_ll[iter - 1] = ll_new;
+        iter++;
+    }
+    for (int i = 0; i < G; i++)
+        if (conv[i] != 0) any_nonconv = 1;
+    if (ctx->world > 1) {  // all(vecMuDispEstConverged == 0) over every shard
+        double v = any_nonconv;
+        CK(cudaMemcpyAsync(ctx->d_xchg, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = do_allreduce(ctx, ctx->d_xchg, 1))) return rc;
+        CK(cudaMemcpyAsync(&v, ctx->d_xchg, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        any_nonconv = v > 0;
+    }
+    *converged = (!any_nonconv && ll_new < ll_old * c->prec_em && ll_new > ll_old) ? 1 : 0;  // :342-347
+    *n_iter = iter - 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calcPostDrop_Matrix
+// ---------------------------------------------------------------------------------------------
+extern "C" int lpb200_post_drop(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids,
+                                int n_ids, double *z) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if ((rc = make_model(ctx, m, M))) return rc;
+    if (M.drop_model == LPB200_DROP_NONE || !p->mat_drop) return set_err(ctx, LPB200_E_ARG, "post_drop needs a drop-out model");
+    if (n_ids <= 0) return 0;
+    const int G = ctx->G, N = ctx->N;
+    for (int r = 0; r < n_ids; r++)
+        if (gene_ids[r] < 0 || gene_ids[r] >= G) return set_err(ctx, LPB200_E_ARG, "gene id out of range");
+    std::vector<double> nat;
+    params_to_nat(ctx, M, p, nat);
+    DevBuf<double> d_nat, d_drop, d_z;
+    DevBuf<int32_t> d_ids;
+    CK(d_nat.alloc(nat.size()));
+    CK(d_drop.alloc((size_t)N * M.q_drop));
+    CK(d_z.alloc((size_t)n_ids * N));
+    CK(d_ids.alloc(n_ids));
+    CK(cudaMemcpyAsync(d_nat.p, nat.data(), sizeof(double) * nat.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_drop.p, p->mat_drop, sizeof(double) * (size_t)N * M.q_drop, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ids.p, gene_ids, sizeof(int32_t) * n_ids, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((N + 255) / 256, n_ids);
+    if (ctx->is_u16) post_drop_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(ctx->D, M, count_view(ctx), d_nat.p, d_drop.p, d_ids.p, n_ids, d_z.p);
+    else post_drop_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(ctx->D, M, count_view(ctx), d_nat.p, d_drop.p, d_ids.p, n_ids, d_z.p);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    CK(cudaMemcpyAsync(z, d_z.p, sizeof(double) * (size_t)n_ids * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LRT (runHypothesisTests.R:81-86): pchisq upper tail + Benjamini-Hochberg.  Host arithmetic on
+// G doubles (negligible); regularised upper incomplete gamma by series / Lentz
+// continued fraction in long double.
+// ---------------------------------------------------------------------------------------------
+static double gamma_q(long double a, long double x) {
+    if (x <= 0) return 1.0;
+    const long double lg = lgammal(a);
+    if (x < a + 1.0L) {  // P by series, Q = 1 - P
+        long double ap = a, sum = 1.0L / a, del = sum;
+        for (int n = 0; n < 100000; n++) {
+            ap += 1.0L;
+            del *= x / ap;
+            sum += del;
+            if (fabsl(del) < fabsl(sum) * 1e-19L) break;
+        }
+        long double P = sum * expl(-x + a * logl(x) - lg);
+        return (double)(1.0L - P);
+    }
+    const long double tiny = 1e-4000L;
+    long double b = x + 1.0L - a, cc = 1.0L / tiny, d = 1.0L / b, h = d;
+    for (int i = 1; i < 100000; i++) {
+        long double an = -(long double)i * ((long double)i - a);
+        b += 2.0L;
+        d = an * d + b;
+        if (fabsl(d) < tiny) d = tiny;
+        cc = b + an / cc;
+        if (fabsl(cc) < tiny) cc = tiny;
+        d = 1.0L / d;
+        long double del = d * cc;
+        h *= del;
+        if (fabsl(del - 1.0L) < 1e-19L) break;
+    }
+    return (double)(expl(-x + a * logl(x) - lg) * h);
+}
+
+static double pchisq_upper(double q, double df) {
+    if (std::isnan(q) || std::isnan(df) || df < 0) return NAN;
+    if (q <= 0) return 1.0;
+    if (df == 0) return 0.0;
+    if (std::isinf(q)) return 0.0;
+    return gamma_q(0.5L * df, 0.5L * q);
+}
+
+extern "C" int lpb200_lrt(const double *ll_full, const double *ll_red, int ddf, int G, double *p, double *padj) {
+    if (!ll_full || !ll_red || !p || !padj || G < 0) return LPB200_E_ARG;
+    std::vector<int> idx;
+    idx.reserve(G);
+    for (int i = 0; i < G; i++) {
+        double dev = 2 * (ll_full[i] - ll_red[i]);
+        p[i] = pchisq_upper(dev, (double)ddf);
+        padj[i] = NAN;
+        if (!std::isnan(p[i])) idx.push_back(i);
+    }
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return p[a] > p[b]; });
+    const int n = (int)idx.size();
+    double cm = INFINITY;
+    for (int k = 0; k < n; k++) {  // p.adjust BH: pmin(1, cummin(n / i * p[o])), i = n..1
+        double v = (double)n / (double)(n - k) * p[idx[k]];
+        if (v < cm) cm = v;
+        padj[idx[k]] = cm < 1.0 ? cm : 1.0;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 DFMA peak probe
+// ---------------------------------------------------------------------------------------------
+extern "C" int lpb200_fp64_peak(lpb200_ctx *ctx, double *tflops) {
+    if (!ctx) return LPB200_E_CUDA;
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 16;
+    DevBuf<double> out;
+    CK(out.alloc((size_t)blocks * threads));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out.p, 1024);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out.p, iters);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaGetLastError());
+    ctx->stats.launches += 4;
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,136 @@
+// lp_math.cuh -- scalar fp64 math of the likelihood: impulse model, logistic drop-out, and the
+// per-observation NB / ZINB log-likelihood terms.  No fast-math; every function is LP_HD so the
+// CPU-only test harness can run the same code.
+#pragma once
+#include "lp_common.cuh"
+
+// evalImpulseModel (evalImpulseModel.R:23-37); p = (beta1, beta2, h0, h1, h2, t1, t2)
+LP_HD double lp_impulse(const double *p, double t) {
+    double d1 = t - p[5];
+    double d2 = t - p[6];
+    return (1.0 / p[3]) * (p[2] + (p[3] - p[2]) * (1.0 / (1.0 + exp(-p[0] * d1)))) *
+           (p[4] + (p[3] - p[4]) * (1.0 / (1.0 + exp(p[1] * d2))));
+}
+
+// evalDropoutModel (evalDropoutModel.R:24-32) given the linear predictor x'theta
+LP_HD double lp_dropout_rate(double lin) {
+    const double off = 0.001;
+    return off + (1.0 - 2.0 * off) * 1.0 / (1.0 + exp(-lin));
+}
+
+// ---- dnbinom(x, mu=, size=phi, log=TRUE) for x >= 1, restating R's nmath dnbinom_mu ->
+// dbinom_raw (C. Loader's saddle-point form: stirlerr + bd0, no cancellation between large
+// terms).  The reference's non-zero terms come from exactly this algorithm (evalLogLik.R:44-48,
+// :136-140), and BFGS paths are sensitive to the last digits of the objective, so the device
+// code follows the same operation sequence instead of an lgamma-difference formula.
+#define LP_LN_SQRT_2PI 0.918938533204672741780329736406
+#define LP_LN_2PI 1.837877066409345483560659472811
+#define LP_SFERR_VALUES                                                                          \
+    {0.0, 0.1534264097200273452913839, 0.08106146679532725821967026, 0.0548141210519176538961387, \
+     0.04134069595540929409382208, 0.03316287351993628748511051, 0.02767792568499833914878929,    \
+     0.02374616365629749597133028, 0.02079067210376509311152277, 0.01848845053267318523077936,    \
+     0.01664469118982119216319487, 0.01513497322191737887351384, 0.01387612882307074799874573,    \
+     0.01281046524292022692425066, 0.01189670994589177009505572, 0.01110455975820691732663076,    \
+     0.01041126526197209649747857, 0.009799416126158803298390373, 0.009255462182712732917728637,  \
+     0.008768700134139385462955047, 0.008330563433362871256469319, 0.007934114564314020547249562, \
+     0.007573675487951840794972024, 0.007244554301320383179546197, 0.006942840107209529865664153, \
+     0.006665247032707682442356181, 0.006408994188004207068439631, 0.006171712263039457647534605, \
+     0.005951370112758847735624416, 0.005746216513010115682026102, 0.00555473355196280137103869}
+static const double lp_sferr_host[31] = LP_SFERR_VALUES;
+#ifdef __CUDACC__
+__constant__ double lp_sferr_dev[31] = LP_SFERR_VALUES;
+#endif
+
+// stirlerr(n) = log(n!) - log(sqrt(2 pi n) (n/e)^n)
+LP_HD double lp_stirlerr(double n) {
+    if (n <= 15.0) {
+        double nn = n + n;
+        if (nn == (double)(int)nn) {
+#ifdef __CUDA_ARCH__
+            return lp_sferr_dev[(int)nn];
+#else
+            return lp_sferr_host[(int)nn];
+#endif
+        }
+        return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - LP_LN_SQRT_2PI;
+    }
+    const double S0 = 0.083333333333333333333, S1 = 0.00277777777777777777778, S2 = 0.00079365079365079365079365,
+                 S3 = 0.000595238095238095238095238, S4 = 0.0008417508417508417508417508;
+    double nn = n * n;
+    if (n > 500.0) return (S0 - S1 / nn) / n;
+    if (n > 80.0) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35.0) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+// bd0(x, np) = x log(x/np) + np - x
+LP_HD double lp_bd0(double x, double np) {
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * v;
+        if (fabs(s) < 2.2250738585072014e-308) return s;
+        double ej = 2.0 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            double s1 = s + ej / (double)((j << 1) + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+// Part of dnbinom_mu that depends on (x, phi) only; tabulated per evaluation point when phi is
+// one scalar per gene.  n = x + phi and xm = n - phi are formed as R forms them (so the loss of
+// digits of n - phi at huge phi is reproduced).
+LP_HD double lp_nb_xphi_part(double x, double phi) {
+    double n = x + phi;
+    double xm = n - phi;
+    double lf = LP_LN_2PI + log(phi) + log1p(-phi / n);
+    return log(phi / (phi + x)) + (lp_stirlerr(n) - lp_stirlerr(phi) - lp_stirlerr(xm)) - 0.5 * lf;
+}
+
+// Part that depends on mu: -bd0(phi, n p) - bd0(n - phi, n q)
+LP_HD double lp_nb_mu_part(double x, double mu, double phi) {
+    double n = x + phi;
+    double p = phi / (phi + mu), q = mu / (phi + mu);
+    if (p == 0.0 || q == 0.0) return -INFINITY;  // dbinom_raw: R_D__0
+    return -lp_bd0(phi, n * p) - lp_bd0(n - phi, n * q);
+}
+
+// Non-zero observation: dnbinom(x, mu, size=phi, log) [+ log(1-pi)], floored
+// (evalLogLik.R:44-49 NB, :135-142 ZINB).  xphi = lp_nb_xphi_part(x, phi) (possibly from a
+// table), l1mpi = log(1-pi) or 0 for NB.
+LP_HD double lp_ll_nonzero(double x, double xphi, double mu, double phi, double l1mpi) {
+    double v = l1mpi + (xphi + lp_nb_mu_part(x, mu, phi));
+    return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
+}
+
+// Zero observation of the NB model: phi*(log(phi) - log(phi+mu)), floored (evalLogLik.R:40-42)
+LP_HD double lp_ll_zero_nb(double mu, double phi, double logphi) {
+    double v = phi * (logphi - log(phi + mu));
+    return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
+}
+
+// Zero observation of the ZINB model: log((1-pi)*(phi/(phi+mu))^phi + pi), floored
+// (evalLogLik.R:125-132).  The ratio is formed exactly as the reference forms it, so the rounding
+// of phi/(phi+mu) at huge phi is reproduced; the power is exp(phi*log(ratio)).
+LP_HD double lp_ll_zero_zinb(double mu, double phi, double pi) {
+    double r = phi / (phi + mu);
+    double nb0 = exp(phi * log(r));
+    double v = log((1.0 - pi) * nb0 + pi);
+    return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
+}
+
+// posterior of drop-out at a zero (calcPostDrop.R:27-45)
+LP_HD double lp_post_drop_zero(double mu, double phi, double pi) {
+    double nb0 = exp(phi * log(phi / (phi + mu)));
+    return pi / (pi + (1.0 - pi) * nb0);
+}
+
+LP_HD double lp_clamp(double v, double lo, double hi) {
+    if (v < lo) v = lo;
+    if (v > hi) v = hi;
+    return v;
+}

@@ -323,8 +323,25 @@ static inline double pi_at(const lpb200_design *d, const lpb200_model *m, const 
 
 /* evalLogLikGene -> evalLogLikZINB / evalLogLikNB for one gene (evalLogLik.R:30-53,107-149,202-228):
  * zeros and non-zeros are summed separately (R sum = long double accumulation) */
+/* Sensitivity knob (tests only): 0 = R on x86 (sum() accumulates in 80-bit long double),
+ * 1 = R built without long double (plain double accumulation).  Both are legitimate R
+ * behaviours; the spread between them is the reference algorithm's own numerical conditioning. */
+static int g_sum_mode = 0;
+void lporacle_set_sum_mode(int mode) { g_sum_mode = mode; }
+
 static double ll_gene(const int32_t *x, int N, const double *mu, const double *sf, const double *disp,
                       const double *pi) {
+    if (g_sum_mode == 1) {
+        double dz = 0.0, dnz = 0.0;
+        for (int j = 0; j < N; j++) {
+            int32_t xj = x[j];
+            if (xj < 0) continue;
+            double mus = sf ? mu[j] * sf[j] : mu[j] * 1.0;
+            double v = lporacle_ll_zinb_obs((double)xj, mus, disp[j], pi ? pi[j] : -1.0);
+            if (xj == 0) dz += v; else dnz += v;
+        }
+        return dz + dnz;
+    }
     long double sz = 0.0L, snz = 0.0L;
     for (int j = 0; j < N; j++) {
         int32_t xj = x[j];

@@ -43,6 +43,9 @@ int lporacle_post_drop(const int32_t *counts, const lpb200_design *d, const lpb2
                        const lpb200_params *p, const int32_t *gene_ids, int n_ids, double *z);
 int lporacle_lrt(const double *ll_full, const double *ll_red, int ddf, int G, double *p, double *padj);
 
+/* 0 (default): long double sums as R on x86; 1: double sums (R without long double) */
+void lporacle_set_sum_mode(int mode);
+
 /* scalar pieces exposed for known-answer tests */
 double lporacle_dnbinom_mu_log(double x, double size, double mu);
 double lporacle_pchisq_upper(double q, double df);
