@@ -1,0 +1,75 @@
+"""Gene-sharded multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The path shards by gene: fitMuDisp, evalLogLikMatrix, the impulse starts and the
+LRT are independent per gene and need no collective.  The per-cell drop-out fit (fitPi) sums
+over ALL genes of a cell, so each lock-step BFGS round all-reduces the N x 2q block of partial
+log-likelihood sums; the EM loop all-reduces one scalar per iteration.  The CUDA library calls
+back into ``make_allreduce``'s closure for those; torch.distributed (NCCL over NVLink on GPUs,
+gloo in the CPU tests) does the transport.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_genes: int, world: int):
+    """Contiguous gene blocks, sizes differing by at most one."""
+    base, extra = divmod(n_genes, world)
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+    return bounds
+
+
+class _CudaF64View:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+def make_allreduce(group=None):
+    """all-reduce(sum) callback for Engine.set_collective on CUDA buffers."""
+    import torch
+    import torch.distributed as dist
+
+    def allreduce(ptr: int, count: int, stream: int):
+        t = torch.as_tensor(_CudaF64View(ptr, count), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    return allreduce
+
+
+def allreduce_host(arr: np.ndarray, group=None) -> np.ndarray:
+    """Sum a host array over the shards (gloo in tests; used for per-rank metadata)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy()
+
+
+def global_min(value: float, group=None) -> float:
+    """min over shards, e.g. of rowMeans for the logistic_ofMu offset (initialiseDropModel.R:80)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return float(t.cpu()[0])
+
+
+def gather_genes(local: np.ndarray, group=None) -> np.ndarray:
+    """Concatenate per-shard gene-indexed arrays (axis 0) on every rank: the all-gather of
+    G x p parameter rows / LL / convergence codes at the end of a fit."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    local = np.ascontiguousarray(local)
+    if world == 1:
+        return local
+    objs = [None] * world
+    dist.all_gather_object(objs, local, group=group)
+    return np.concatenate(objs, axis=0)

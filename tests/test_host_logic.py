@@ -1,0 +1,148 @@
+"""CPU-only tests of the host side: C-ABI surface, ns(), simulator, data preparation, LRT."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lineagepulse_b200 as lp
+from lineagepulse_b200 import _cabi as A
+from lineagepulse_b200.splines import _bspline_basis_all, ns
+from tests.helpers import golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lpb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(lpb200_[a-z0-9_]+)\s*\(", hdr)) - {"lpb200_allreduce_fn"})
+    assert len(declared) >= 25
+    lib = C.CDLL(A.default_library_path())
+    for name in declared:
+        assert hasattr(lib, name), f"liblpb200.so does not export {name}"
+    bound = A.declare_product_prototypes(lib)
+    assert sorted(bound) == declared  # the ctypes mirror covers exactly the header
+    assert lib.lpb200_abi_version() == 1
+    ctl = A.Control()
+    lib.lpb200_default_control(C.byref(ctl))
+    assert (ctl.maxit_mudisp, ctl.maxit_pi, ctl.max_cycles) == (1000, 10000, 20)  # fitModel.R:164-175
+    assert ctl.reltol_mudisp == 1e-8 and ctl.ndeps == 1e-3 and ctl.prec_em == 1 - 1e-4
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lp.LPB200Error):
+        lp.Engine(0)
+    with pytest.raises(lp.LPB200Error):
+        lp.evalLogLikMatrix(np.ones((3, 4), dtype=np.int32), {"lsMuModelGlobal": {"strMuModel": "constant", "vecNormConst": np.ones(4)}, "matMuModel": np.ones((3, 1))},
+                            {"lsDispModelGlobal": {"strDispModel": "constant"}, "matDispModel": np.ones((3, 1))},
+                            {"lsDropModelGlobal": {"strDropModel": "none"}})
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "lineagepulse_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "lporacle" not in src and "liblporacle" not in src, f
+                assert not re.search(r"^\s*(from|import)\s+\S*oracle", src, re.M), f
+                assert not re.search(r"#include\s+\"[^\"]*oracle", src), f
+
+
+def test_ns_against_scipy_and_r_pattern():
+    from scipy.interpolate import BSpline
+    x = np.linspace(0, 1, 200)
+    B = ns(x, 6)
+    assert B.shape == (200, 6) and np.linalg.matrix_rank(B) == 6
+    # the boundary row R prints for this design
+    assert np.allclose(B[-1], [0, 0, 0, -1 / 7, 3 / 7, 5 / 7], atol=1e-12)
+    ik = np.quantile(x, np.linspace(0, 1, 6)[1:-1])
+    t = np.sort(np.r_[np.repeat([0.0, 1.0], 4), ik])
+    D = BSpline.design_matrix(x, t, 3).toarray()
+    assert np.abs(D - _bspline_basis_all(t, x, 4)).max() < 1e-14
+    # natural: second derivative vanishes at both boundary knots for every basis function
+    d2 = BSpline(t, np.eye(len(t) - 4), 3).derivative(2)
+    q = np.linalg.qr(_bspline_basis_all(t, np.array([0.0, 1.0]), 4, deriv=2).T, mode="complete")[0][:, 2:]
+    assert np.abs(d2(np.array([0.0, 1 - 1e-13])) @ q).max() < 1e-6
+    # constants and linear functions lie in the span
+    for y in (np.ones_like(x), x):
+        c = np.linalg.lstsq(B, y, rcond=None)[0]
+        assert np.abs(B @ c - y).max() < 1e-12
+    rng = np.random.default_rng(0)
+    xr = np.sort(rng.uniform(size=57))
+    assert ns(xr, 4).shape == (57, 4) and np.linalg.matrix_rank(ns(xr, 4)) == 4
+
+
+def test_simulator_recipe():
+    s = lp.simulateContinuousDataSet(300, 20, 20, 20, scaMumax=100, scaSDMuAmplitude=3,
+                                     vecGeneWiseDropoutRates=np.full(60, 0.1), seed=7)
+    X = s["counts"]
+    assert X.shape == (60, 300) and X.min() >= 0
+    assert np.allclose(s["annot"]["continuous"], np.arange(300) / 299)  # simulateDataSet.R:123
+    zero_frac = (X == 0).mean()
+    assert 0.1 <= zero_frac <= 0.6
+    s2 = lp.simulateContinuousDataSet(300, 20, 20, 20, scaMumax=100, scaSDMuAmplitude=3,
+                                      vecGeneWiseDropoutRates=np.full(60, 0.1), seed=7)
+    assert np.array_equal(X, s2["counts"])
+    with pytest.raises(ValueError):
+        lp.simulateContinuousDataSet(10, 1, 1, 1, vecGeneWiseDropoutRates=np.full(5, 0.1))
+    with pytest.raises(ValueError):
+        lp.simulateContinuousDataSet(10, 1, 1, 1)
+
+
+def test_first_appearance_index():
+    lab, idx = A.first_appearance_index(np.array(["b", "a", "b", "c", "a"]))
+    assert list(lab) == ["b", "a", "c"] and list(idx) == [0, 1, 0, 2, 1]  # match(v, unique(v)) - 1
+
+
+def test_process_sc_data_filters_and_errors():
+    X = np.array([[0, 0, 0, 0], [1, 0, 2, 0], [0, 0, 5, 1]], dtype=float)
+    X[1, 3] = np.nan  # NA silently becomes 0 on sparsification (processSCData.R:262-264)
+    annot = {"cell": np.array(["a", "b", "c", "d"]), "continuous": np.array([0.0, 0.3, np.nan, 1.0])}
+    r = lp.processSCData(X, annot, strMuModel="impulse", boolVerbose=False, rownames=["g1", "g2", "g3"])
+    obj = r["objLP"]
+    # cell c (NA pseudotime) dropped, then all-zero gene g1 and all-zero cell b dropped
+    assert list(obj.matCountsProc.rownames) == ["g2", "g3"]
+    assert list(obj.matCountsProc.colnames) == ["a", "d"]
+    assert list(obj.vecAllGenes) == ["g1", "g2", "g3"]
+    assert np.array_equal(obj.matCountsProc.dense(), np.array([[1, 0], [0, 1]]))
+    assert "1 out of 4 cells did not have a continuous covariate" in obj.strReport
+    with pytest.raises(lp.LineagePulseError, match="non-integer"):
+        lp.processSCData(np.array([[0.5, 1.0]]), {"cell": np.array(["a", "b"])}, strMuModel="constant", boolVerbose=False)
+    with pytest.raises(lp.LineagePulseError, match="negative"):
+        lp.processSCData(np.array([[-1.0, 1.0]]), {"cell": np.array(["a", "b"])}, strMuModel="constant", boolVerbose=False)
+    with pytest.raises(lp.LineagePulseError, match="strMuModel not recognised"):
+        lp.processSCData(X, annot, strMuModel="MM", boolVerbose=False)  # processSCData.R:231-234
+    with pytest.raises(lp.LineagePulseError, match="Supply dfAnnotation"):
+        lp.processSCData(X, None, strMuModel="constant", boolVerbose=False)
+
+
+def test_object_accessors():
+    obj = lp.LineagePulseObject(strReport="x", vecAllGenes=np.array(["g"]))
+    assert "dfResults" in obj.names() and obj["strReport"] == "x"
+    from lineagepulse_b200 import api
+    assert api.strReport(obj) == "x" and api.vecAllGenes(obj)[0] == "g" and api.lsDropModel(obj) is None
+    assert obj.boolFixedPopulations is False
+
+
+def test_lrt_host_arithmetic_vs_mpmath_and_oracle(oracle):
+    rng = np.random.default_rng(0)
+    for df in (1, 3, 6, 7):
+        q = np.r_[rng.exponential(8, 100), 0.0, -2.0, 900.0, 1600.0]
+        llr = -rng.uniform(100, 1000, len(q))
+        llf = llr + q / 2
+        p, padj = lp.lrt(llf, llr, df)
+        po, pao = oracle.lrt(llf, llr, df)
+        assert np.allclose(p, po, rtol=1e-12, atol=1e-300)
+        assert np.allclose(padj, pao, rtol=1e-12, atol=1e-300)
+        assert p[-3] == 1.0 and p[-4] == 1.0  # deviance <= 0 => p = 1
+    for r in golden("pchisq_upper.json"):
+        p, _ = lp.lrt(np.array([r["q"] / 2]), np.array([0.0]), r["df"])
+        assert abs(p[0] - r["value"]) <= 1e-12 * r["value"] + 1e-300
+    p, padj = lp.lrt(np.array([1.0, np.nan, 3.0]), np.array([0.0, 0.0, 0.0]), 2)
+    assert np.isnan(p[1]) and np.isnan(padj[1]) and not np.isnan(padj[0])
