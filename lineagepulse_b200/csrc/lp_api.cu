@@ -26,6 +26,8 @@ struct lpb200_ctx {
     void *d_counts = nullptr;  // uint16_t or int32_t, gene-major
     size_t pitch = 0;
     int32_t *d_xmax = nullptr;
+    uint32_t *d_perm = nullptr;   // [G][pitch] non-zero cells first, then zeros
+    int32_t *d_nnz = nullptr, *d_nobs = nullptr;
     std::vector<double> row_means;
     int global_max = 0;
     // design
@@ -46,6 +48,7 @@ struct lpb200_ctx {
     lpb200_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int use_table = 1;
+    int no_fastpath = 0;   // LPB200_NO_FASTPATH=1: always run the generic evaluator (testing)
 };
 
 static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
@@ -125,6 +128,8 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
     }
     const char *e = getenv("LPB200_NO_TABLE");
     if (e && atoi(e)) c->use_table = 0;
+    e = getenv("LPB200_NO_FASTPATH");
+    if (e && atoi(e)) c->no_fastpath = 1;
     return c;
 }
 
@@ -142,6 +147,9 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     free_design(c);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->d_xmax) cudaFree(c->d_xmax);
+    if (c->d_perm) cudaFree(c->d_perm);
+    if (c->d_nnz) cudaFree(c->d_nnz);
+    if (c->d_nobs) cudaFree(c->d_nobs);
     if (c->d_xchg) cudaFree(c->d_xchg);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -194,6 +202,14 @@ static int finish_counts(lpb200_ctx *ctx, int32_t *d_i32, int G, int N, size_t p
     CK(cudaMalloc((void **)&ctx->d_xmax, sizeof(int32_t) * G));
     row_stats_kernel<<<G, 256, 0, ctx->stream>>>(d_i32, G, N, pitch, d_mean.p, ctx->d_xmax);
     CK(cudaGetLastError());
+    if (ctx->d_perm) cudaFree(ctx->d_perm);
+    if (ctx->d_nnz) cudaFree(ctx->d_nnz);
+    if (ctx->d_nobs) cudaFree(ctx->d_nobs);
+    CK(cudaMalloc((void **)&ctx->d_perm, sizeof(uint32_t) * (size_t)G * pitch));
+    CK(cudaMalloc((void **)&ctx->d_nnz, sizeof(int32_t) * G));
+    CK(cudaMalloc((void **)&ctx->d_nobs, sizeof(int32_t) * G));
+    build_perm_kernel<<<G, 256, 0, ctx->stream>>>(d_i32, G, N, pitch, ctx->d_perm, ctx->d_nnz, ctx->d_nobs);
+    CK(cudaGetLastError());
     ctx->row_means.resize(G);
     std::vector<int32_t> xmax(G);
     CK(cudaMemcpyAsync(ctx->row_means.data(), d_mean.p, sizeof(double) * G, cudaMemcpyDeviceToHost, ctx->stream));
@@ -218,7 +234,7 @@ static int finish_counts(lpb200_ctx *ctx, int32_t *d_i32, int G, int N, size_t p
         ctx->d_counts = d_i32;
         ctx->is_u16 = false;
     }
-    ctx->stats.launches += 2;
+    ctx->stats.launches += 3;
     ctx->have_starts = false;
     return 0;
 }
@@ -491,6 +507,9 @@ static CountView count_view(const lpb200_ctx *ctx) {
     C.ptr = ctx->d_counts;
     C.pitch = ctx->pitch;
     C.xmax = ctx->d_xmax;
+    C.perm = ctx->d_perm;
+    C.nnz = ctx->d_nnz;
+    C.nobs = ctx->d_nobs;
     return C;
 }
 
@@ -687,13 +706,38 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
     if ((rc = setup_drop(ctx, M, p, grid, A, B))) return rc;
     const size_t smem = sizeof(FitShared);
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->is_u16) {
-        CK(cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fit_mudisp_kernel<uint16_t><<<grid, threads, smem, ctx->stream>>>(A);
-    } else {
-        CK(cudaFuncSetAttribute(fit_mudisp_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fit_mudisp_kernel<int32_t><<<grid, threads, smem, ctx->stream>>>(A);
-    }
+    // specialised kernels for the hot configurations, generic kernel otherwise
+    const bool fast = !ctx->no_fastpath && lp_disp_is_scalar(D, M) && D.n_conf_mu == 0 &&
+                      (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE) &&
+                      (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
+#define LP_LAUNCH_FIT(KERNEL)                                                                               \
+    do {                                                                                                    \
+        CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        KERNEL<<<grid, threads, smem, ctx->stream>>>(A);                                                   \
+    } while (0)
+#define LP_LAUNCH_FIT_CT(CT)                                                                                \
+    do {                                                                                                    \
+        if (fast) {                                                                                         \
+            const bool zinb = M.drop_model == LPB200_DROP_LOGISTIC;                                         \
+            if (M.mu_model == LPB200_MU_IMPULSE) {                                                          \
+                if (zinb) LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, true>));                 \
+                else LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, false>));                     \
+            } else {                                                                                        \
+                if (zinb) LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_CONST, true>));                   \
+                else LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_CONST, false>));                       \
+            }                                                                                               \
+        } else {                                                                                            \
+            LP_LAUNCH_FIT((fit_mudisp_kernel<CT, -1, false>));                                              \
+        }                                                                                                   \
+    } while (0)
+    if (ctx->is_u16) LP_LAUNCH_FIT_CT(uint16_t);
+    else LP_LAUNCH_FIT_CT(int32_t);
+#undef LP_LAUNCH_FIT_CT
+#undef LP_LAUNCH_FIT
+    if (getenv("LPB200_DEBUG"))
+        fprintf(stderr, "[lpb200] fit_mudisp: %s kernel (%s counts), mu=%d drop=%d items=%zu grid=%d threads=%d smem=%zu\n",
+                fast ? "specialised" : "generic", ctx->is_u16 ? "u16" : "i32", M.mu_model, M.drop_model, n_items, grid,
+                threads, smem);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->stats.launches++;
@@ -803,6 +847,13 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
         pi_start_kernel<<<nb, 128, 0, ctx->stream>>>(A, d_drop.p, c->maxit_pi, c->reltol_pi);
         CK(cudaGetLastError());
         ctx->stats.launches++;
+        // Lock-step rounds.  The active-cell count is read back (a host sync) every round at first
+        // and every 4th round once most cells have stopped; on one GPU the last few cells are handed
+        // to pi_tail_kernel, which finishes their BFGS without any further host round trips.
+        const int tail_threshold = 256;
+        int since_check = 0, check_every = 1;
+        DevBuf<int> d_list;
+        CK(d_list.alloc(N));
         for (long round = 0;; round++) {
             CK(cudaMemsetAsync(d_active.p, 0, sizeof(int), ctx->stream));
             if (ctx->is_u16) launch_pi_eval<uint16_t>(ctx, A);
@@ -814,10 +865,23 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
             pi_advance_kernel<<<nb, 128, 0, ctx->stream>>>(A);
             CK(cudaGetLastError());
             ctx->stats.launches += 3;
+            if (++since_check < check_every) continue;
+            since_check = 0;
             int active = 0;
             CK(cudaMemcpyAsync(&active, d_active.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             if (active == 0) break;
+            if (round >= 8) check_every = 4;
+            if (ctx->world == 1 && active <= tail_threshold) {
+                CK(cudaMemsetAsync(d_active.p, 0, sizeof(int), ctx->stream));
+                pi_compact_kernel<<<nb, 128, 0, ctx->stream>>>(A, d_list.p, d_active.p);
+                CK(cudaGetLastError());
+                if (ctx->is_u16) pi_tail_kernel<uint16_t><<<active, 256, 0, ctx->stream>>>(A, d_list.p);
+                else pi_tail_kernel<int32_t><<<active, 256, 0, ctx->stream>>>(A, d_list.p);
+                CK(cudaGetLastError());
+                ctx->stats.launches += 2;
+                break;
+            }
         }
         CK(d_ll.alloc(N));
         CK(d_conv.alloc(N));

@@ -27,6 +27,12 @@
 #define LP_FIT_THREADS 256
 #define LP_PI_NP 8        // max drop-out parameters per cell (1 + ofMu + LPB200_MAX_PI_PRED)
 #define LP_PI_KP 16       // points per cell per round (2q)
+#ifndef LP_FAST_MINBLOCKS
+#define LP_FAST_MINBLOCKS 4     // CTAs per SM the specialised fit kernels are compiled for (register cap 64)
+#endif
+#ifndef LP_GENERIC_MINBLOCKS
+#define LP_GENERIC_MINBLOCKS 4
+#endif
 
 __device__ __forceinline__ int lp_load_count(const uint16_t *r, int j) {
     unsigned v = r[j];
@@ -41,9 +47,14 @@ __device__ __forceinline__ double lp_warp_sum(double v) {
 }
 
 struct CountView {
-    const void *ptr;      // gene-major, row pitch in elements
+    const void *ptr;       // gene-major, row pitch in elements
     size_t pitch;
-    const int32_t *xmax;  // per gene
+    const int32_t *xmax;   // per gene
+    // per gene: cell indices with the non-zero observations first, then the zeros (NA left out), so that
+    // the lanes of a warp take the same zero / non-zero branch except in one boundary warp per pass
+    const uint32_t *perm;  // [G][pitch]
+    const int32_t *nnz;    // [G] number of non-zero observations
+    const int32_t *nobs;   // [G] non-zero + zero observations
 };
 
 struct FitArgs {
@@ -119,8 +130,11 @@ __device__ void lp_eval_points(const FitArgs &A, FitShared &S, const CT *row, in
     }
     double acc = 0.0;
     const int stride = nwarps * cpw;
-    for (int j = warp * cpw + slot; j < N; j += stride) {
+    const uint32_t *perm = A.C.perm + (size_t)gene * A.C.pitch;
+    const int nobs = A.C.nobs[gene];
+    for (int r = warp * cpw + slot; r < nobs; r += stride) {
         if (!active) continue;
+        const int j = (int)perm[r];
         int x = lp_load_count(row, j);
         double s = D.sf ? D.sf[j] : 1.0;
         double pf = 0.0, l1 = 0.0;
@@ -131,6 +145,89 @@ __device__ void lp_eval_points(const FitArgs &A, FitShared &S, const CT *row, in
         acc += lp_cell_ll(D, M, P, A.drop, gene, j, x, s, pf, l1, phi_s, logphi_s, tabp, tab_len);
     }
     // combine the cell slots of the warp, then the warps (fixed order => deterministic)
+    for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane < npad && lane < nk) S.red[lane * LP_MAX_WARPS + warp] = acc;
+    __syncthreads();
+    if (tid < nk) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += S.red[tid * LP_MAX_WARPS + w];
+        out_vals[tid] = s;
+    }
+    __syncthreads();
+}
+
+// Specialised evaluator for the hot configurations (BASELINE configs C1-C3): constant or impulse
+// mean, one scalar dispersion per gene, no mean confounders, drop-out "none" or gene-wise fixed
+// ("logistic").  Same arithmetic as lp_cell_ll -- operation for operation, so results are
+// bit-identical to the generic path -- but the lane's point lives in registers and the dead model
+// branches are gone (the generic kernel is ~13k SASS instructions, far beyond the I-cache).
+__device__ __noinline__ double lp_nb_xphi_part_cold(double x, double phi) { return lp_nb_xphi_part(x, phi); }
+#define LP_MU_FAST_CONST 0
+#define LP_MU_FAST_IMPULSE 1
+template <typename CT, int MU, bool ZINB>
+__device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *row, int gene, int xmax, int nk, int ntabs,
+                                    double *out_vals, const double *pi_ptr, const double *l1m_ptr) {
+    const DevDesign &D = A.D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int N = D.N;
+    int tab_len = 0;
+    if (A.use_table && ntabs > 0) {
+        int want = min(xmax + 1, LP_TAB);
+        if ((long long)ntabs * want * 2 <= (long long)nk * N) tab_len = want;
+    }
+    if (tab_len > 0) {
+        for (int e = tid; e < ntabs * tab_len; e += blockDim.x) {
+            int tsel = e / tab_len, x = e - tsel * tab_len;
+            S.tab[tsel][x] = (x == 0) ? 0.0 : lp_nb_xphi_part((double)x, S.tab_phi[tsel]);
+        }
+    }
+    __syncthreads();
+    int npad = 1;
+    while (npad < nk) npad <<= 1;
+    const int cpw = 32 / npad;
+    const int k = lane & (npad - 1);
+    const int slot = lane / npad;
+    const bool active = k < nk;
+    const PointNat &P = S.pts[active ? k : 0];
+    const double phi = P.disp[0];
+    const double logphi = log(phi);
+    const double p0 = P.mu[0];
+    double b2 = 0, h0 = 0, h1 = 0, h2 = 0, t1 = 0, t2 = 0, inv_h1 = 0;
+    if (MU == LP_MU_FAST_IMPULSE) {
+        b2 = P.mu[1]; h0 = P.mu[2]; h1 = P.mu[3]; h2 = P.mu[4]; t1 = P.mu[5]; t2 = P.mu[6];
+        inv_h1 = 1.0 / h1;
+    }
+    const double *tabp = tab_len > 0 ? S.tab[S.tab_of_point[active ? k : 0]] : nullptr;
+    const double *sf = D.sf;
+    const double *tt = D.t;
+    double acc = 0.0;
+    const int stride = nwarps * cpw;
+    const uint32_t *perm = A.C.perm + (size_t)gene * A.C.pitch;
+    const int nobs = A.C.nobs[gene], nnz = A.C.nnz[gene];
+    if (active) {
+        for (int r = warp * cpw + slot; r < nobs; r += stride) {
+            const int j = (int)perm[r];
+            const int x = (r < nnz) ? lp_load_count(row, j) : 0;
+            double mu;
+            if (MU == LP_MU_FAST_IMPULSE) {
+                const double t = tt[j];
+                mu = inv_h1 * (h0 + (h1 - h0) * (1.0 / (1.0 + exp(-p0 * (t - t1))))) *
+                     (h2 + (h1 - h2) * (1.0 / (1.0 + exp(b2 * (t - t2)))));
+            } else {
+                mu = p0;
+            }
+            const double mus = sf ? mu * sf[j] : mu;
+            double v;
+            if (x == 0) {
+                v = ZINB ? lp_ll_zero_zinb(mus, phi, pi_ptr[j]) : lp_ll_zero_nb(mus, phi, logphi);
+            } else {
+                const double xd = (double)x;
+                const double xphi = (x < tab_len) ? tabp[x] : lp_nb_xphi_part_cold(xd, phi);  // cold: keeps lgamma out of the loop body
+                v = lp_ll_nonzero(xd, xphi, mus, phi, ZINB ? l1m_ptr[j] : 0.0);
+            }
+            acc += v;
+        }
+    }
     for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane < npad && lane < nk) S.red[lane * LP_MAX_WARPS + warp] = acc;
     __syncthreads();
@@ -166,8 +263,10 @@ __device__ void lp_fixed_pi(const FitArgs &A, int gene, const double *&pi_ptr, c
     l1m_ptr = ls;
 }
 
-template <typename CT>
-__global__ void __launch_bounds__(LP_FIT_THREADS)
+// MU = -1: generic evaluator (any model); MU = LP_MU_FAST_*: specialised evaluator, ZINB selects
+// the fixed-drop-out ZINB terms over the NB terms.
+template <typename CT, int MU, bool ZINB>
+__global__ void __launch_bounds__(LP_FIT_THREADS, (MU >= 0) ? LP_FAST_MINBLOCKS : LP_GENERIC_MINBLOCKS)
 fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
     extern __shared__ __align__(16) unsigned char lp_smem[];
     FitShared &S = *reinterpret_cast<FitShared *>(lp_smem);
@@ -215,7 +314,10 @@ fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
                 }
                 __syncthreads();
                 const int ntabs = (req == LP_REQ_F) ? 1 : (base == 0 ? 3 : 1);
-                lp_eval_points<CT>(A, S, row, gene, xmax, kc, ntabs, S.vals + base, pi_ptr, l1m_ptr);
+                if constexpr (MU >= 0)
+                    lp_eval_points_fast<CT, MU, ZINB>(A, S, row, gene, xmax, kc, ntabs, S.vals + base, pi_ptr, l1m_ptr);
+                else
+                    lp_eval_points<CT>(A, S, row, gene, xmax, kc, ntabs, S.vals + base, pi_ptr, l1m_ptr);
             }
             if (tid == 0) bfgs_advance(S.st, S.vals);
             __syncthreads();
@@ -565,6 +667,96 @@ __global__ void pi_finish_kernel(PiArgs A, double *drop_out, double *ll, int *co
     evals[j] = st.evals;
 }
 
+// Tail of the lock-step loop (single GPU): the few cells that still iterate are finished by one
+// CTA each, which runs the remaining BFGS iterations inside the kernel (no launch / host round
+// trip per objective evaluation).  The CTA strides over the genes of its cell; reads of the
+// gene-major matrix are strided, which is irrelevant for a handful of cells.
+__global__ void pi_compact_kernel(PiArgs A, int *list, int *count) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.D.N) return;
+    if (A.states[j].req != LP_REQ_NONE) list[atomicAdd(count, 1)] = j;
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ PiArgs A, const int *list) {
+    __shared__ double s_vals[LP_PI_KP];
+    __shared__ double s_red[LP_PI_KP * 8];
+    __shared__ double s_coef[LP_PI_KP][LP_PI_NP];
+    __shared__ int s_nk;
+    const DevDesign &D = A.D;
+    const DevModel &M = A.M;
+    const int j = list[blockIdx.x];
+    const int q = M.q_drop, n_nat = lp_n_nat(M);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    PiState &st = A.states[j];
+    const double s = D.sf ? D.sf[j] : 1.0;
+    const CT *base = reinterpret_cast<const CT *>(A.C.ptr);
+    for (;;) {
+        if (tid == 0) {
+            int req = st.req;
+            int nk = (req == LP_REQ_F) ? 1 : (req == LP_REQ_GRAD ? 2 * q : 0);
+            for (int k = 0; k < nk; k++) {
+                double th[LP_PI_NP];
+                for (int i = 0; i < q; i++) th[i] = st.b[i];
+                if (req == LP_REQ_GRAD) {
+                    int c = bfgs_grad_coord(k);
+                    th[c] = bfgs_grad_point(st.b[c], k, A.ndeps);
+                }
+                lp_pi_transform(M.drop_model, q, th, s_coef[k]);
+            }
+            s_nk = nk;
+        }
+        __syncthreads();
+        const int nk = s_nk;
+        if (nk == 0) break;
+        double acc[LP_PI_KP];
+#pragma unroll
+        for (int k = 0; k < LP_PI_KP; k++) acc[k] = 0.0;
+        for (int i = tid; i < D.G; i += blockDim.x) {
+            const int x = lp_load_count(base + (size_t)i * A.C.pitch, j);
+            if (x < 0) continue;
+            PointNat P;
+            lp_nat_load(M, A.nat + (size_t)i * n_nat, P);
+            const double mu = lp_mu_at(D, M, P, j);
+            const double phi = lp_disp_at(D, M, P, j);
+            const double mus = mu * s;
+            const double lmu = (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) ? log(mu) : 0.0;
+            double core;
+            if (x == 0) core = exp(phi * log(phi / (phi + mus)));
+            else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
+#pragma unroll
+            for (int k = 0; k < LP_PI_KP; k++) {
+                if (k < nk) {
+                    int u = 1;
+                    double lin = 1.0 * s_coef[k][0];
+                    if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * s_coef[k][u++];
+                    for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * s_coef[k][u];
+                    double pi = lp_dropout_rate(lin);
+                    double v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
+                    if (v < LP_LL_FLOOR) v = LP_LL_FLOOR;
+                    acc[k] += v;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < LP_PI_KP; k++) {
+            if (k < nk) {
+                double v = lp_warp_sum(acc[k]);
+                if (lane == 0) s_red[k * 8 + warp] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < nk) {
+            double v = 0.0;
+            for (int w = 0; w < nwarps; w++) v += s_red[tid * 8 + w];
+            s_vals[tid] = v;
+        }
+        __syncthreads();
+        if (tid == 0) bfgs_advance(st, s_vals);
+        __syncthreads();
+    }
+}
+
 // ForAllCells: total[k] = sum_j vals[k][j]  (one CTA per point, fixed order)
 __global__ void pi_total_kernel(const double *vals, int N, double *total) {
     __shared__ double sh[32];
@@ -627,6 +819,61 @@ __global__ void scatter_csc_kernel(const int32_t *p, const int32_t *i, const dou
     for (int e = p[j] + threadIdx.x; e < p[j + 1]; e += blockDim.x) {
         double v = x[e];
         out[(size_t)i[e] * pitch + j] = isnan(v) ? LPB200_NA_COUNT : (int32_t)llrint(v);
+    }
+}
+
+// stable partition of one gene's cells: non-zero observations first, then zeros; NA dropped
+__global__ void __launch_bounds__(256) build_perm_kernel(const int32_t *c, int G, int N, size_t pitch, uint32_t *perm,
+                                                         int32_t *nnz_out, int32_t *nobs_out) {
+    __shared__ int sh_nz[8], sh_z[8];
+    __shared__ int run_nz, run_z, tot_nz;
+    const int g = blockIdx.x;
+    const int32_t *row = c + (size_t)g * pitch;
+    uint32_t *out = perm + (size_t)g * pitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cnt = 0;
+    for (int j = tid; j < N; j += blockDim.x) cnt += row[j] > 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) sh_nz[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) t += sh_nz[w];
+        tot_nz = t;
+        run_nz = 0;
+        run_z = 0;
+    }
+    __syncthreads();
+    const int nnz = tot_nz;
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int j = base + tid;
+        const int v = (j < N) ? row[j] : -1;
+        const unsigned bnz = __ballot_sync(0xffffffffu, v > 0), bz = __ballot_sync(0xffffffffu, v == 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (lane == 0) {
+            sh_nz[warp] = __popc(bnz);
+            sh_z[warp] = __popc(bz);
+        }
+        __syncthreads();
+        int off_nz = run_nz, off_z = run_z;
+        for (int w = 0; w < warp; w++) {
+            off_nz += sh_nz[w];
+            off_z += sh_z[w];
+        }
+        if (v > 0) out[off_nz + __popc(bnz & lt)] = (uint32_t)j;
+        else if (v == 0) out[nnz + off_z + __popc(bz & lt)] = (uint32_t)j;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 0; w < 8; w++) {
+                run_nz += sh_nz[w];
+                run_z += sh_z[w];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        nnz_out[g] = nnz;
+        nobs_out[g] = nnz + run_z;
     }
 }
 
