@@ -1,0 +1,235 @@
+/*
+ * lp_rshim.c -- the `.Call` shim between the LineagePulse R package and liblpb200.so.
+ *
+ * R stays the host language (BASELINE.json north_star); this file contains no arithmetic: it
+ * unpacks the R lists that fitMuDisp / fitPi / evalLogLikMatrix / fitModel already receive
+ * (fitMeanDispersion.R:853-859, fitDropout.R:418-422, evalLogLik.R:307-313, fitModel.R:137-158),
+ * calls the C ABI of include/lpb200.h and re-packs the results under the reference's names.
+ *
+ * STATUS: R is not installed in the build image, so this file is compile-checked against
+ * r_shim/fake_R/Rinternals.h (a minimal stand-in declaring only the API used here) by
+ * tests/test_host_logic.py::test_r_shim_compiles; it has NOT been run against a real R.
+ * Build inside the package with:  PKG_LIBS = -L<dir> -llpb200   (src/Makevars)
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+
+#include "../include/lpb200.h"
+
+/* ---- helpers -------------------------------------------------------------------------------- */
+static SEXP list_get(SEXP list, const char *name) {
+    SEXP names = getAttrib(list, R_NamesSymbol);
+    for (int i = 0; i < LENGTH(list); i++)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+    return R_NilValue;
+}
+static const double *dbl_or_null(SEXP x) { return (x == R_NilValue) ? NULL : REAL(x); }
+
+static void ctx_finalizer(SEXP ptr) {
+    lpb200_ctx *ctx = (lpb200_ctx *)R_ExternalPtrAddr(ptr);
+    if (ctx) {
+        lpb200_destroy(ctx);
+        R_ClearExternalPtr(ptr);
+    }
+}
+static lpb200_ctx *ctx_of(SEXP ptr) {
+    lpb200_ctx *ctx = (lpb200_ctx *)R_ExternalPtrAddr(ptr);
+    if (!ctx) error("LineagePulse: GPU context was released");
+    return ctx;
+}
+static void check(lpb200_ctx *ctx, int rc) { /* any optimiser error aborts, as fitMeanDispersion.R:384-389 */
+    if (rc != 0) error("LineagePulse (lpb200, code %d): %s", rc, lpb200_last_error(ctx));
+}
+
+/* ---- context + data ------------------------------------------------------------------------- */
+/* .Call("lp_create", device) -> external pointer with finalizer */
+SEXP lp_create(SEXP device) {
+    lpb200_ctx *ctx = lpb200_create(asInteger(device));
+    if (!ctx) error("LineagePulse: no usable CUDA device (there is no CPU fallback)");
+    SEXP ptr = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* .Call("lp_load_counts_csc", ctx, dim, p, i, x): slots of the dgCMatrix matCountsProc */
+SEXP lp_load_counts_csc(SEXP sctx, SEXP dim, SEXP p, SEXP i, SEXP x) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    check(ctx, lpb200_load_counts_csc(ctx, INTEGER(dim)[0], INTEGER(dim)[1], INTEGER(p), INTEGER(i), REAL(x)));
+    return R_NilValue;
+}
+/* .Call("lp_load_counts_dense", ctx, matrix) */
+SEXP lp_load_counts_dense(SEXP sctx, SEXP mat) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    SEXP dim = getAttrib(mat, R_DimSymbol);
+    check(ctx, lpb200_load_counts_dense(ctx, INTEGER(dim)[0], INTEGER(dim)[1], REAL(mat)));
+    return R_NilValue;
+}
+
+/* the design travels as a named list built by the R wrapper from lsMuModelGlobal / lsDispModelGlobal /
+ * lsDropModel (R/lpb200_wrappers.R::lpDesign); index vectors arrive 1-based and are shifted here */
+static int *shift_idx(SEXP v) {
+    if (v == R_NilValue) return NULL;
+    int n = LENGTH(v);
+    int *out = (int *)R_alloc(n, sizeof(int));
+    for (int k = 0; k < n; k++) out[k] = INTEGER(v)[k] - 1;
+    return out;
+}
+static void fill_design(SEXP lst, lpb200_design *d) {
+    memset(d, 0, sizeof(*d));
+    d->n_genes = asInteger(list_get(lst, "n_genes"));
+    d->n_cells = asInteger(list_get(lst, "n_cells"));
+    d->size_factors = dbl_or_null(list_get(lst, "vecNormConst"));
+    d->pseudotime = dbl_or_null(list_get(lst, "vecContinuousCovar"));
+    d->group_idx = shift_idx(list_get(lst, "vecidxGroups"));
+    d->n_groups = asInteger(list_get(lst, "scaNGroups"));
+    SEXP b = list_get(lst, "matSplineBasisMu");
+    if (b != R_NilValue) { d->spline_basis_mu = REAL(b); d->k_spline_mu = INTEGER(getAttrib(b, R_DimSymbol))[1]; }
+    b = list_get(lst, "matSplineBasisDisp");
+    if (b != R_NilValue) { d->spline_basis_disp = REAL(b); d->k_spline_disp = INTEGER(getAttrib(b, R_DimSymbol))[1]; }
+    d->impulse_basis = dbl_or_null(list_get(lst, "matImpulseBasis")); /* ns(t, df = 4, intercept = TRUE) */
+    SEXP nb = list_get(lst, "vecNBatchesMu");
+    if (nb != R_NilValue) {
+        d->n_conf_mu = LENGTH(nb);
+        for (int c = 0; c < d->n_conf_mu; c++) d->n_batches_mu[c] = INTEGER(nb)[c];
+        d->batch_idx_mu = shift_idx(list_get(lst, "vecidxBatchAssignMu")); /* unlist(lsvecidxBatchAssign) */
+    }
+    nb = list_get(lst, "vecNBatchesDisp");
+    if (nb != R_NilValue) {
+        d->n_conf_disp = LENGTH(nb);
+        for (int c = 0; c < d->n_conf_disp; c++) d->n_batches_disp[c] = INTEGER(nb)[c];
+        d->batch_idx_disp = shift_idx(list_get(lst, "vecidxBatchAssignDisp"));
+    }
+    b = list_get(lst, "matPiConstPredictors");
+    if (b != R_NilValue) { d->pi_const_pred = REAL(b); d->n_pi_pred = INTEGER(getAttrib(b, R_DimSymbol))[1]; }
+}
+SEXP lp_set_design(SEXP sctx, SEXP lst) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    lpb200_design d;
+    fill_design(lst, &d);
+    check(ctx, lpb200_set_design(ctx, &d));
+    return R_NilValue;
+}
+
+static lpb200_model model_of(SEXP m) { /* integer(4): mu, disp, drop, drop-fit-group codes */
+    lpb200_model mm = {INTEGER(m)[0], INTEGER(m)[1], INTEGER(m)[2], INTEGER(m)[3]};
+    return mm;
+}
+/* params: list(matMuModel, matBatchMu (cbind of lsmatBatchModel), matDispModel, matBatchDisp, matDropoutLinModel);
+ * the matrices are duplicated by the R wrapper before the call, so writing into them is safe */
+static lpb200_params params_of(SEXP p) {
+    lpb200_params pp;
+    pp.mat_mu = (double *)dbl_or_null(list_get(p, "matMuModel"));
+    pp.batch_mu = (double *)dbl_or_null(list_get(p, "matBatchMu"));
+    pp.mat_disp = (double *)dbl_or_null(list_get(p, "matDispModel"));
+    pp.batch_disp = (double *)dbl_or_null(list_get(p, "matBatchDisp"));
+    pp.mat_drop = (double *)dbl_or_null(list_get(p, "matDropoutLinModel"));
+    return pp;
+}
+
+/* ---- evalLogLikMatrix (evalLogLik.R:307) ---------------------------------------------------- */
+SEXP lp_eval_loglik(SEXP sctx, SEXP model, SEXP params, SEXP n_genes) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    lpb200_model m = model_of(model);
+    lpb200_params p = params_of(params);
+    SEXP ll = PROTECT(allocVector(REALSXP, asInteger(n_genes)));
+    check(ctx, lpb200_eval_loglik(ctx, &m, &p, REAL(ll)));
+    UNPROTECT(1);
+    return ll;
+}
+
+/* ---- fitMuDisp (fitMeanDispersion.R:853): returns list(params, vecConvergence, vecLL) -------- */
+SEXP lp_fit_mudisp(SEXP sctx, SEXP model, SEXP params, SEXP n_genes) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    lpb200_model m = model_of(model);
+    lpb200_params p = params_of(params);
+    lpb200_control c;
+    lpb200_default_control(&c);
+    int G = asInteger(n_genes);
+    SEXP ll = PROTECT(allocVector(REALSXP, G)), conv = PROTECT(allocVector(INTSXP, G));
+    check(ctx, lpb200_fit_mudisp(ctx, &m, &p, &c, REAL(ll), INTEGER(conv)));
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, params);
+    SET_VECTOR_ELT(out, 1, conv);
+    SET_VECTOR_ELT(out, 2, ll);
+    UNPROTECT(3);
+    return out;
+}
+
+/* ---- fitPi (fitDropout.R:418) --------------------------------------------------------------- */
+SEXP lp_fit_pi(SEXP sctx, SEXP model, SEXP params, SEXP n_out) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    lpb200_model m = model_of(model);
+    lpb200_params p = params_of(params);
+    lpb200_control c;
+    lpb200_default_control(&c);
+    int n = asInteger(n_out);
+    SEXP ll = PROTECT(allocVector(REALSXP, n)), conv = PROTECT(allocVector(INTSXP, n));
+    check(ctx, lpb200_fit_pi(ctx, &m, &p, &c, REAL(ll), INTEGER(conv)));
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, params);
+    SET_VECTOR_ELT(out, 1, conv);
+    SET_VECTOR_ELT(out, 2, ll);
+    UNPROTECT(3);
+    return out;
+}
+
+/* ---- fitModel (fitModel.R:137): whole EM loop in one call ----------------------------------- */
+SEXP lp_fit_model(SEXP sctx, SEXP model, SEXP params, SEXP fit_drop, SEXP n_genes) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    lpb200_model m = model_of(model);
+    lpb200_params p = params_of(params);
+    lpb200_control c;
+    lpb200_default_control(&c);
+    int G = asInteger(n_genes);
+    SEXP em = PROTECT(allocVector(REALSXP, c.max_cycles)), ll = PROTECT(allocVector(REALSXP, G));
+    SEXP conv = PROTECT(allocVector(INTSXP, G)), info = PROTECT(allocVector(REALSXP, 3));
+    int32_t n_iter = 0, converged = 0;
+    double ll_init = 0;
+    check(ctx, lpb200_fit_model(ctx, &m, &p, asLogical(fit_drop), &c, R_NaN, REAL(em), &n_iter, &converged, &ll_init,
+                                REAL(ll), INTEGER(conv)));
+    for (int k = 0; k < c.max_cycles; k++)
+        if (ISNAN(REAL(em)[k])) REAL(em)[k] = NA_REAL; /* vecEMLogLikModel <- array(NA, ...) fitModel.R:184 */
+    REAL(info)[0] = n_iter;
+    REAL(info)[1] = converged;
+    REAL(info)[2] = ll_init;
+    SEXP out = PROTECT(allocVector(VECSXP, 5));
+    SET_VECTOR_ELT(out, 0, params);
+    SET_VECTOR_ELT(out, 1, em);
+    SET_VECTOR_ELT(out, 2, ll);
+    SET_VECTOR_ELT(out, 3, conv);
+    SET_VECTOR_ELT(out, 4, info);
+    UNPROTECT(5);
+    return out;
+}
+
+/* ---- LRT of runDEAnalysis (runHypothesisTests.R:81-86) -------------------------------------- */
+SEXP lp_lrt(SEXP ll_full, SEXP ll_red, SEXP ddf) {
+    int G = LENGTH(ll_full);
+    SEXP p = PROTECT(allocVector(REALSXP, G)), padj = PROTECT(allocVector(REALSXP, G));
+    if (lpb200_lrt(REAL(ll_full), REAL(ll_red), asInteger(ddf), G, REAL(p), REAL(padj)) != 0) error("lpb200_lrt failed");
+    SEXP out = PROTECT(allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, p);
+    SET_VECTOR_ELT(out, 1, padj);
+    UNPROTECT(3);
+    return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"lp_create", (DL_FUNC)&lp_create, 1},
+    {"lp_load_counts_csc", (DL_FUNC)&lp_load_counts_csc, 5},
+    {"lp_load_counts_dense", (DL_FUNC)&lp_load_counts_dense, 2},
+    {"lp_set_design", (DL_FUNC)&lp_set_design, 2},
+    {"lp_eval_loglik", (DL_FUNC)&lp_eval_loglik, 4},
+    {"lp_fit_mudisp", (DL_FUNC)&lp_fit_mudisp, 4},
+    {"lp_fit_pi", (DL_FUNC)&lp_fit_pi, 4},
+    {"lp_fit_model", (DL_FUNC)&lp_fit_model, 5},
+    {"lp_lrt", (DL_FUNC)&lp_lrt, 3},
+    {NULL, NULL, 0}};
+
+void R_init_LineagePulse(DllInfo *dll) {
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

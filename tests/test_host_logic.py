@@ -146,3 +146,16 @@ def test_lrt_host_arithmetic_vs_mpmath_and_oracle(oracle):
         assert abs(p[0] - r["value"]) <= 1e-12 * r["value"] + 1e-300
     p, padj = lp.lrt(np.array([1.0, np.nan, 3.0]), np.array([0.0, 0.0, 0.0]), 2)
     assert np.isnan(p[1]) and np.isnan(padj[1]) and not np.isnan(padj[0])
+
+
+def test_r_shim_compiles():
+    """R is absent from the image: the .Call shim is compile-checked (syntax + prototypes of the C ABI)
+    against r_shim/fake_R, a stand-in declaring only the R API it uses."""
+    import subprocess
+    subprocess.check_call(["gcc", "-std=gnu11", "-fsyntax-only", "-Werror=implicit-function-declaration",
+                           "-Werror=incompatible-pointer-types", "-I", os.path.join(ROOT, "r_shim", "fake_R"),
+                           os.path.join(ROOT, "r_shim", "lp_rshim.c")])
+    src = open(os.path.join(ROOT, "r_shim", "lp_rshim.c")).read()
+    for sym in ("lpb200_fit_mudisp", "lpb200_fit_pi", "lpb200_eval_loglik", "lpb200_fit_model", "lpb200_lrt",
+                "lpb200_load_counts_csc", "lpb200_set_design"):
+        assert sym in src
