@@ -14,6 +14,7 @@ Group / batch index vectors are 0-based here (R: 1-based).
 """
 from __future__ import annotations
 
+import sys
 import time
 import warnings
 
@@ -33,6 +34,11 @@ _GROUP = A.DROP_FIT_GROUPS
 
 class LineagePulseError(Exception):
     """R's stop()."""
+
+
+def message(*args):
+    """R's message(): diagnostics go to stderr, never to stdout."""
+    print(*args, file=sys.stderr)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -374,7 +380,7 @@ def fitModel(matCounts, dfAnnotation, vecConfoundersMu=None, vecConfoundersDisp=
         codes = ",".join(str(c) for c in np.unique(r["conv"][r["conv"] != 0]))
         strReport += f"(Mean-) Dispersion estimation did not converge in {n_bad} cases [codes: {codes}].\n"
     if boolVerbose:
-        print(strReport, end="")
+        message(strReport.rstrip("\n"))
     ncyc = ctl.max_cycles if boolFitDrop else 1
     return {"lsMuModel": lsMu, "lsDispModel": lsDisp, "lsDropModel": lsDrop,
             "boolConvergenceModel": r["converged"], "vecEMLogLikModel": r["em_ll"][:ncyc],
@@ -489,7 +495,7 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
     if "cell" not in dfProc:
         dfProc["cell"] = colnames[cell_idx]
     if boolVerbose:
-        print(strReport, end="")
+        message(strReport.rstrip("\n"))
     objLP = LineagePulseObject(
         dfAnnotationProc=dfProc, matCountsProc=CountMatrix(m, rownames[gene_idx], colnames[cell_idx], device),
         scaDFSplinesDisp=scaDFSplinesDisp, scaDFSplinesMu=scaDFSplinesMu, strReport=strReport,
@@ -504,7 +510,7 @@ def calcNormConst(objLP, vecNormConstExternal):
     if vecNormConstExternal is not None:
         v = np.array(vecNormConstExternal, dtype=np.float64)
     else:
-        print("# All size factors are set to one.")
+        message("# All size factors are set to one.")
         v = np.ones(objLP.matCountsProc.shape[1])
     if np.any(v == 0):
         warnings.warn("WARNING IN LINEAGEPULSE: Found size factors==0. Setting these to 1.")
@@ -536,7 +542,7 @@ def fitLPModels(objLP, matPiConstPredictors=None, strMuModel="constant", strDisp
     def log(msg):
         objLP.strReport = (objLP.strReport or "") + msg + "\n"
         if boolVerbose:
-            print(msg)
+            message(msg)
 
     log(f"### a) Fit ZINB model A ({nameA}) with noise model.")
     fitA = fitModel(lsDropModel=None, strMuModel=strMuModelA, strDispModel=strDispModelA, strDropModel=strDropModel,
@@ -640,7 +646,7 @@ def runLineagePulse(counts, dfAnnotation=None, vecConfoundersMu=None, vecConfoun
     def log(msg):
         objLP.strReport += msg + "\n"
         if boolVerbose:
-            print(msg)
+            message(msg)
 
     log("--- Compute normalisation constants:")
     objLP.vecNormConst = calcNormConst(objLP, ls["vecNormConstExternalProc"])
@@ -657,7 +663,7 @@ def runLineagePulse(counts, dfAnnotation=None, vecConfoundersMu=None, vecConfoun
     objLP = runDEAnalysis(objLP)
     objLP.strReport += "Finished runLineagePulse()."
     if boolVerbose:
-        print("Finished runLineagePulse().")
+        message("Finished runLineagePulse().")
     return objLP
 
 
