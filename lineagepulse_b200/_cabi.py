@@ -20,6 +20,8 @@ DISP_CONSTANT, DISP_SPLINES, DISP_GROUPS = 0, 2, 3
 DROP_NONE, DROP_LOGISTIC, DROP_LOGISTIC_OFMU = 0, 1, 2
 DROPFIT_PERCELL, DROPFIT_FORALLCELLS = 0, 1
 NA_COUNT = -1
+EXPAND_MEAN, EXPAND_DISP, EXPAND_DROP, EXPAND_POSTDROP, EXPAND_NORMDATA = 0, 1, 2, 3, 4
+EXPAND_NO_DEPTH, EXPAND_NO_BATCH = 16, 32
 
 E_ARG, E_CUDA, E_STATE, E_NOTSUP, E_NONFINITE, E_COMM = -1, -2, -3, -4, -5, -6
 
@@ -287,6 +289,7 @@ def declare_product_prototypes(lib):
         "lpb200_fit_model": (C.c_int, [vp, P(Model), P(Params), C.c_int, P(Control), C.c_double,
                                        c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_int32_p]),
         "lpb200_post_drop": (C.c_int, [vp, P(Model), P(Params), c_int32_p, C.c_int, c_double_p]),
+        "lpb200_expand_fits": (C.c_int, [vp, P(Model), P(Params), c_int32_p, C.c_int, C.c_int, c_double_p]),
         "lpb200_lrt": (C.c_int, [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
         "lpb200_row_means": (C.c_int, [vp, c_double_p]),
         "lpb200_get_stats": (C.c_int, [vp, P(Stats)]),

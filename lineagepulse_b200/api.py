@@ -670,7 +670,66 @@ def runLineagePulse(counts, dfAnnotation=None, vecConfoundersMu=None, vecConfoun
 # ---------------------------------------------------------------------------------------------
 # fit extraction (getFits.R): post-hoc expansions for user-selected genes
 # ---------------------------------------------------------------------------------------------
-def getPostDrop(vecGeneIDs, objLP):
+def _check_ids(counts, vecGeneIDs, what):
+    ids = np.asarray(vecGeneIDs)
+    if not np.issubdtype(ids.dtype, np.integer) and not np.all(np.isin(ids, counts.rownames)):
+        raise LineagePulseError(f"ERROR {what}(): Not all vecGeneIDs were rownames of the model matrices")
+    return _gene_indices(counts, vecGeneIDs)
+
+
+def _no_drop(lsDropModel=None):
+    return lsDropModel if lsDropModel is not None else _NB_DROP
+
+
+def _dummy_disp(counts):
+    return {"matDispModel": np.ones((counts.shape[0], 1)), "lsmatBatchModel": None,
+            "lsDispModelGlobal": {"strDispModel": "constant"}}
+
+
+def getNormData(matCounts, lsMuModel, vecGeneIDs, boolDepth=True, boolBatch=True):
+    """getFits.R:52-98: counts divided by size factors and / or batch factors."""
+    if not boolDepth and not boolBatch:
+        warnings.warn("No normalisation chosen")
+    counts, eng, design, model = _prepare(matCounts, lsMuModel, _dummy_disp(_as_counts(matCounts)), _NB_DROP)
+    ids = _check_ids(counts, vecGeneIDs, "getNormData")
+    p = _params_from_models(design, model, lsMuModel, _dummy_disp(counts), _NB_DROP)
+    what = A.EXPAND_NORMDATA | (0 if boolDepth else A.EXPAND_NO_DEPTH) | (0 if boolBatch else A.EXPAND_NO_BATCH)
+    return eng.expand_fits(model, p, ids, what)
+
+
+def getFitsMean(lsMuModel, vecGeneIDs=None, matCounts=None):
+    """getFits.R:134-154 (decompressMeansByGene; no size factors).  ``matCounts`` names the GPU-resident
+    matrix whose context evaluates the expansion (the R function needs none because it runs on the host)."""
+    counts = _as_counts(matCounts)
+    counts, eng, design, model = _prepare(counts, lsMuModel, _dummy_disp(counts), _NB_DROP)
+    ids = _check_ids(counts, vecGeneIDs, "getFitsMean")
+    return eng.expand_fits(model, _params_from_models(design, model, lsMuModel, _dummy_disp(counts), _NB_DROP), ids,
+                           A.EXPAND_MEAN)
+
+
+def getFitsDispersion(lsDispModel, vecGeneIDs=None, matCounts=None):
+    """getFits.R:196-216."""
+    counts = _as_counts(matCounts)
+    lsMu = {"matMuModel": np.ones((counts.shape[0], 1)), "lsmatBatchModel": None,
+            "lsMuModelGlobal": {"strMuModel": "constant", "vecNormConst": None,
+                                "vecContinuousCovar": lsDispModel["lsDispModelGlobal"].get("vecPseudotime")}}
+    counts, eng, design, model = _prepare(counts, lsMu, lsDispModel, _NB_DROP)
+    ids = _check_ids(counts, vecGeneIDs, "getFitsDispersion")
+    return eng.expand_fits(model, _params_from_models(design, model, lsMu, lsDispModel, _NB_DROP), ids, A.EXPAND_DISP)
+
+
+def getFitsDropout(lsMuModel, lsDropModel, vecGeneIDs=None, matCounts=None):
+    """getFits.R:261-288."""
+    counts = _as_counts(matCounts)
+    counts, eng, design, model = _prepare(counts, lsMuModel, _dummy_disp(counts), lsDropModel)
+    ids = _check_ids(counts, vecGeneIDs, "getFitsDropout")
+    return eng.expand_fits(model, _params_from_models(design, model, lsMuModel, _dummy_disp(counts), lsDropModel), ids,
+                           A.EXPAND_DROP)
+
+
+def getPostDrop(matCounts, lsMuModel, lsDispModel, lsDropModel, vecGeneIDs):
     """getFits.R:340-363."""
-    return calcPostDrop_Matrix(objLP.matCountsProc, objLP.lsMuModelH1, objLP.lsDispModelH1, objLP.lsDropModel,
-                               vecIDs=vecGeneIDs)
+    counts = _as_counts(matCounts)
+    if not np.issubdtype(np.asarray(vecGeneIDs).dtype, np.integer) and not np.all(np.isin(vecGeneIDs, counts.rownames)):
+        raise LineagePulseError("ERROR getFitsDropout(): Not all vecGeneIDs were rownames of matCounts.")
+    return calcPostDrop_Matrix(counts, lsMuModel, lsDispModel, lsDropModel, vecIDs=vecGeneIDs)

@@ -1114,13 +1114,17 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
 // ---------------------------------------------------------------------------------------------
 // calcPostDrop_Matrix
 // ---------------------------------------------------------------------------------------------
-extern "C" int lpb200_post_drop(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids,
-                                int n_ids, double *z) {
+extern "C" int lpb200_expand_fits(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids,
+                                  int n_ids, int what, double *z) {
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
     if ((rc = make_model(ctx, m, M))) return rc;
-    if (M.drop_model == LPB200_DROP_NONE || !p->mat_drop) return set_err(ctx, LPB200_E_ARG, "post_drop needs a drop-out model");
+    const int kind = what & 15;
+    if (kind > LPB200_EXPAND_NORMDATA) return set_err(ctx, LPB200_E_ARG, "unknown expansion %d", what);
+    const bool needs_drop = kind == LPB200_EXPAND_DROP || kind == LPB200_EXPAND_POSTDROP;
+    if (needs_drop && (M.drop_model == LPB200_DROP_NONE || !p->mat_drop))
+        return set_err(ctx, LPB200_E_ARG, "this expansion needs a drop-out model");
     if (n_ids <= 0) return 0;
     const int G = ctx->G, N = ctx->N;
     for (int r = 0; r < n_ids; r++)
@@ -1130,20 +1134,26 @@ extern "C" int lpb200_post_drop(lpb200_ctx *ctx, const lpb200_model *m, const lp
     DevBuf<double> d_nat, d_drop, d_z;
     DevBuf<int32_t> d_ids;
     CK(d_nat.alloc(nat.size()));
-    CK(d_drop.alloc((size_t)N * M.q_drop));
+    CK(d_drop.alloc((size_t)N * std::max(1, M.q_drop)));
     CK(d_z.alloc((size_t)n_ids * N));
     CK(d_ids.alloc(n_ids));
     CK(cudaMemcpyAsync(d_nat.p, nat.data(), sizeof(double) * nat.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_drop.p, p->mat_drop, sizeof(double) * (size_t)N * M.q_drop, cudaMemcpyHostToDevice, ctx->stream));
+    if (needs_drop)
+        CK(cudaMemcpyAsync(d_drop.p, p->mat_drop, sizeof(double) * (size_t)N * M.q_drop, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_ids.p, gene_ids, sizeof(int32_t) * n_ids, cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((N + 255) / 256, n_ids);
-    if (ctx->is_u16) post_drop_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(ctx->D, M, count_view(ctx), d_nat.p, d_drop.p, d_ids.p, n_ids, d_z.p);
-    else post_drop_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(ctx->D, M, count_view(ctx), d_nat.p, d_drop.p, d_ids.p, n_ids, d_z.p);
+    if (ctx->is_u16) expand_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(ctx->D, M, count_view(ctx), d_nat.p, d_drop.p, d_ids.p, n_ids, what, d_z.p);
+    else expand_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(ctx->D, M, count_view(ctx), d_nat.p, d_drop.p, d_ids.p, n_ids, what, d_z.p);
     CK(cudaGetLastError());
     ctx->stats.launches++;
     CK(cudaMemcpyAsync(z, d_z.p, sizeof(double) * (size_t)n_ids * N, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+extern "C" int lpb200_post_drop(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids,
+                                int n_ids, double *z) {
+    return lpb200_expand_fits(ctx, m, p, gene_ids, n_ids, LPB200_EXPAND_POSTDROP, z);
 }
 
 // ---------------------------------------------------------------------------------------------

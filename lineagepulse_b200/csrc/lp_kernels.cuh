@@ -768,11 +768,11 @@ __global__ void pi_total_kernel(const double *vals, int N, double *total) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// calcPostDrop_Matrix
+// calcPostDrop_Matrix and the fit extraction of getFits.R
 // ---------------------------------------------------------------------------------------------
 template <typename CT>
-__global__ void post_drop_kernel(DevDesign D, DevModel M, CountView C, const double *nat, const double *drop,
-                                 const int32_t *ids, int n_ids, double *z) {
+__global__ void expand_kernel(DevDesign D, DevModel M, CountView C, const double *nat, const double *drop,
+                              const int32_t *ids, int n_ids, int what, double *z) {
     __shared__ PointNat P;
     int r = blockIdx.y;
     int i = ids[r];
@@ -780,15 +780,39 @@ __global__ void post_drop_kernel(DevDesign D, DevModel M, CountView C, const dou
     __syncthreads();
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= D.N) return;
-    int x = lp_load_count(reinterpret_cast<const CT *>(C.ptr) + (size_t)i * C.pitch, j);
+    const int kind = what & 15;
     double out;
-    if (x < 0) out = NAN;
-    else if (x > 0) out = 0.0;
-    else {
-        double mu = lp_mu_at(D, M, P, j);   // no size factor (calcPostDrop.R:110)
-        double phi = lp_disp_at(D, M, P, j);
-        double pi = lp_dropout_rate(lp_drop_lin(D, M, drop, i, j, mu));
-        out = lp_post_drop_zero(mu, phi, pi);
+    if (kind == LPB200_EXPAND_MEAN) {
+        out = lp_mu_at(D, M, P, j);
+    } else if (kind == LPB200_EXPAND_DISP) {
+        out = lp_disp_at(D, M, P, j);
+    } else if (kind == LPB200_EXPAND_DROP) {
+        out = lp_dropout_rate(lp_drop_lin(D, M, drop, i, j, lp_mu_at(D, M, P, j)));
+    } else {
+        int x = lp_load_count(reinterpret_cast<const CT *>(C.ptr) + (size_t)i * C.pitch, j);
+        if (kind == LPB200_EXPAND_NORMDATA) {  // getNormData (getFits.R:52-98)
+            if (x < 0) out = NAN;
+            else {
+                out = (double)x;
+                if (!(what & LPB200_EXPAND_NO_DEPTH)) out = out / (D.sf ? D.sf[j] : 1.0);
+                if (!(what & LPB200_EXPAND_NO_BATCH)) {
+                    double bp = 1.0;
+                    int o = 0;
+                    for (int c = 0; c < D.n_conf_mu; c++) {
+                        bp = bp * P.bmu[o + D.bidx_mu[(size_t)c * D.N + j]];
+                        o += D.nb_mu[c];
+                    }
+                    out = out / bp;
+                }
+            }
+        } else if (x < 0) out = NAN;
+        else if (x > 0) out = 0.0;
+        else {
+            double mu = lp_mu_at(D, M, P, j);   // no size factor (calcPostDrop.R:110)
+            double phi = lp_disp_at(D, M, P, j);
+            double pi = lp_dropout_rate(lp_drop_lin(D, M, drop, i, j, mu));
+            out = lp_post_drop_zero(mu, phi, pi);
+        }
     }
     z[r + (size_t)j * n_ids] = out;
 }

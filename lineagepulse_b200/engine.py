@@ -176,6 +176,15 @@ class Engine:
                                               len(ids), z.ctypes.data_as(A.c_double_p)))
         return z
 
+    def expand_fits(self, model, params, gene_ids, what):
+        """getFits.R expansions (what = _cabi.EXPAND_*): n_ids x N matrix."""
+        ids = np.ascontiguousarray(gene_ids, dtype=np.int32)
+        z = np.zeros((len(ids), self.n_cells), order="F")
+        ps = params.as_struct()
+        self._check(self.lib.lpb200_expand_fits(self.ctx, C.byref(model), C.byref(ps), ids.ctypes.data_as(A.c_int32_p),
+                                                len(ids), int(what), z.ctypes.data_as(A.c_double_p)))
+        return z
+
     def stats(self):
         s = A.Stats()
         self._check(self.lib.lpb200_get_stats(self.ctx, C.byref(s)))

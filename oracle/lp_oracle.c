@@ -1347,6 +1347,40 @@ int lporacle_post_drop(const int32_t *counts, const lpb200_design *d, const lpb2
     return 0;
 }
 
+/* getFits.R:52-363: getFitsMean / getFitsDispersion / getFitsDropout / getNormData */
+int lporacle_expand_fits(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
+                         const lpb200_params *p, const int32_t *gene_ids, int n_ids, int what, double *z) {
+    int N = d->n_cells;
+    int kind = what & 15;
+    if (kind == LPB200_EXPAND_POSTDROP) return lporacle_post_drop(counts, d, m, p, gene_ids, n_ids, z);
+    for (int r = 0; r < n_ids; r++) {
+        int i = gene_ids[r];
+        gene_nat g;
+        load_gene_nat(d, m, p, i, &g);
+        for (int j = 0; j < N; j++) {
+            double out;
+            if (kind == LPB200_EXPAND_MEAN) out = mu_at(d, m->mu_model, &g, j);
+            else if (kind == LPB200_EXPAND_DISP) out = disp_at(d, m->disp_model, &g, j);
+            else if (kind == LPB200_EXPAND_DROP) out = pi_at(d, m, p->mat_drop, i, j, mu_at(d, m->mu_model, &g, j));
+            else { /* getNormData */
+                int32_t x = counts[(size_t)i * N + j];
+                if (x < 0) out = NAN;
+                else {
+                    out = (double)x;
+                    if (!(what & LPB200_EXPAND_NO_DEPTH)) out = out / (d->size_factors ? d->size_factors[j] : 1.0);
+                    if (!(what & LPB200_EXPAND_NO_BATCH)) {
+                        double bp = 1.0;
+                        for (int c = 0; c < d->n_conf_mu; c++) bp = bp * g.bmu[c][d->batch_idx_mu[(size_t)c * N + j]];
+                        out = out / bp;
+                    }
+                }
+            }
+            z[r + (size_t)j * n_ids] = out;
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------- */
 /* LRT + BH (runHypothesisTests.R:81-86)                                      */
 /* ------------------------------------------------------------------------- */

@@ -41,6 +41,8 @@ int lporacle_fit_model(const int32_t *counts, const lpb200_design *d, const lpb2
                        uint64_t *fn_evals, int nthreads);
 int lporacle_post_drop(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
                        const lpb200_params *p, const int32_t *gene_ids, int n_ids, double *z);
+int lporacle_expand_fits(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
+                         const lpb200_params *p, const int32_t *gene_ids, int n_ids, int what, double *z);
 int lporacle_lrt(const double *ll_full, const double *ll_red, int ddf, int G, double *p, double *padj);
 
 /* 0 (default): long double sums as R on x86; 1: double sums (R without long double) */

@@ -40,6 +40,7 @@ class Oracle:
                                          dp, ip, ip, dp, dp, ip, u64p, C.c_int]
         L.lporacle_post_drop.argtypes = [ip, P(A.Design), P(A.Model), P(A.Params), ip, C.c_int, dp]
         L.lporacle_lrt.argtypes = [dp, dp, C.c_int, C.c_int, dp, dp]
+        L.lporacle_expand_fits.argtypes = [ip, P(A.Design), P(A.Model), P(A.Params), ip, C.c_int, C.c_int, dp]
         L.lporacle_dnbinom_mu_log.argtypes = [C.c_double] * 3
         L.lporacle_dnbinom_mu_log.restype = C.c_double
         L.lporacle_pchisq_upper.argtypes = [C.c_double] * 2
@@ -180,6 +181,16 @@ class Oracle:
         self._check(self.lib.lporacle_post_drop(cp, C.byref(design.struct), C.byref(model), C.byref(ps),
                                                 ids.ctypes.data_as(A.c_int32_p), len(ids),
                                                 z.ctypes.data_as(A.c_double_p)))
+        return z
+
+    def expand_fits(self, counts, design, model, params, gene_ids, what):
+        c, cp = self._counts(counts)
+        ids = np.ascontiguousarray(gene_ids, dtype=np.int32)
+        z = np.zeros((len(ids), design.n_cells), order="F")
+        ps = params.as_struct()
+        self._check(self.lib.lporacle_expand_fits(cp, C.byref(design.struct), C.byref(model), C.byref(ps),
+                                                  ids.ctypes.data_as(A.c_int32_p), len(ids), int(what),
+                                                  z.ctypes.data_as(A.c_double_p)))
         return z
 
     def lrt(self, ll_full, ll_red, ddf):
