@@ -345,14 +345,22 @@ def main():
     ker_s = (w["B"]["kernel_ms"] + w["D"]["kernel_ms"]) / 1e3
     achieved = (flop_B + flop_D) / ker_s / 1e12
     share = ker_s * 1e3 / step_ms[-1]
-    count_bytes = 2.0 * G * N  # uint16 gene-major count matrix, read once per fitMuDisp call
+    ct_bytes = 2 if int(X.max()) < 65535 else 4   # the library stores uint16 unless a count needs int32
+    ct_name = "uint16_t" if ct_bytes == 2 else "int32_t"
+    count_bytes = float(ct_bytes) * G * N   # gene-major count matrix, read once per fitMuDisp call
+    perm_bytes = 4.0 * G * N               # per-gene cell permutation (non-zero cells first)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak, "traffic": None,
-                "kernel": "fit_mudisp_kernel<uint16_t> (impulse fits B + D)",
+                "frac": achieved / fp64_peak,
+                # dram__bytes_read + write per launch from profiles/ncu_fit_mudisp_impulse_zinb_r1.csv
+                # (82.7 MB at 1 184 genes x 10 000 cells, u16 counts), scaled to this launch's matrix
+                "traffic": 82.65e6 * (G * N) / (1184.0 * 10000.0) * ((ct_bytes + 4.0) / 6.0),
+                "traffic_unit": "bytes per launch (ncu, scaled by matrix size)",
+                "kernel": f"fit_mudisp_kernel<{ct_name}, impulse> (fits B + D)",
                 "kernel_share_of_step": share,
                 "ole_per_s": (w["B"]["ole"] + w["D"]["ole"]) / ker_s,
                 "peak_source": "FP64 DFMA chain probe measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                "hbm": {"algorithmic_bytes_per_launch": count_bytes, "achieved_GBps": 2 * count_bytes / ker_s / 1e9,
+                "hbm": {"algorithmic_bytes_per_launch": count_bytes + perm_bytes,
+                        "achieved_GBps": 2 * (count_bytes + perm_bytes) / ker_s / 1e9,
                         "peak_GBps": _hbm_peak(), "note": "count bytes are <0.1% of HBM bandwidth: FP64-bound (SURVEY.md F7)"}}
 
     cpu = None
