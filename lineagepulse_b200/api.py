@@ -61,7 +61,6 @@ class CountMatrix:
         self.colnames = np.asarray(colnames if colnames is not None else [f"cell_{j + 1}" for j in range(N)])
         self.device = device
         self._engine = None
-        self._design_key = None
 
     def engine(self) -> Engine:
         if self._engine is None:

@@ -752,6 +752,16 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->stats.kernel_ms += ms;
+    if (getenv("LPB200_DEBUG") && n_starts > 1) {
+        double sum[3] = {0, 0, 0};
+        unsigned mx[3] = {0, 0, 0};
+        for (size_t it = 0; it < n_items; it++) {
+            sum[it % 3] += evals[it];
+            mx[it % 3] = std::max(mx[it % 3], evals[it]);
+        }
+        fprintf(stderr, "[lpb200] evals per start (peak, valley, prior): mean %.0f %.0f %.0f  max %u %u %u  kernel %.1f ms\n",
+                sum[0] / G, sum[1] / G, sum[2] / G, mx[0], mx[1], mx[2], ms);
+    }
     bool nonfinite = false;
     for (int i = 0; i < G; i++) {
         int best = 0;

@@ -7,7 +7,6 @@ a usable CUDA device raises.
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 

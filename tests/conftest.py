@@ -11,6 +11,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the CUDA library is a build artefact (git-ignored): build it in-tree when a fresh checkout lacks it
+    lib = os.path.join(ROOT, "lineagepulse_b200", "liblpb200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "lineagepulse_b200", "csrc")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
