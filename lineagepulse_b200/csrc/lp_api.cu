@@ -68,15 +68,67 @@ static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
             return set_err(ctx, LPB200_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Scratch-buffer pool: cudaMalloc / cudaFree synchronise the device and showed up as 0.3-1 s of
+// host-side jitter per fit; freed scratch blocks are kept per device and reused by later calls.
+struct PoolBlock {
+    void *p;
+    size_t bytes;
+    int device;
+};
+static std::vector<PoolBlock> g_pool;
+static size_t g_pool_bytes = 0;
+static const size_t POOL_CAP_BYTES = (size_t)16 << 30;
+
+static cudaError_t pool_alloc(void **out, size_t bytes, size_t *got) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bytes = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    size_t best = (size_t)-1;
+    for (size_t k = 0; k < g_pool.size(); k++)
+        if (g_pool[k].device == dev && g_pool[k].bytes >= bytes && g_pool[k].bytes <= 2 * bytes + ((size_t)1 << 20) &&
+            (best == (size_t)-1 || g_pool[k].bytes < g_pool[best].bytes))
+            best = k;
+    if (best != (size_t)-1) {
+        *out = g_pool[best].p;
+        *got = g_pool[best].bytes;
+        g_pool_bytes -= g_pool[best].bytes;
+        g_pool.erase(g_pool.begin() + best);
+        return cudaSuccess;
+    }
+    *got = bytes;
+    return cudaMalloc(out, bytes);
+}
+static void pool_free(void *p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_pool_bytes + bytes > POOL_CAP_BYTES) {
+        cudaFree(p);
+        return;
+    }
+    g_pool.push_back(PoolBlock{p, bytes, dev});
+    g_pool_bytes += bytes;
+}
+static void pool_release(int device) {
+    for (size_t k = 0; k < g_pool.size();) {
+        if (g_pool[k].device == device) {
+            cudaFree(g_pool[k].p);
+            g_pool_bytes -= g_pool[k].bytes;
+            g_pool.erase(g_pool.begin() + k);
+        } else {
+            k++;
+        }
+    }
+}
+
 template <typename T>
-struct DevBuf {  // RAII device buffer
+struct DevBuf {  // RAII device scratch buffer (pooled)
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, bytes = 0;
     DevBuf() {}
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) pool_free(p, bytes); }
     cudaError_t alloc(size_t count) {
         n = count;
-        return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+        return pool_alloc((void **)&p, count * sizeof(T), &bytes);
     }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -144,6 +196,8 @@ static void free_design(lpb200_ctx *c) {
 extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    pool_release(c->device);
     free_design(c);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->d_xmax) cudaFree(c->d_xmax);
