@@ -816,6 +816,22 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
         fprintf(stderr, "[lpb200] evals per start (peak, valley, prior): mean %.0f %.0f %.0f  max %u %u %u  kernel %.1f ms\n",
                 sum[0] / G, sum[1] / G, sum[2] / G, mx[0], mx[1], mx[2], ms);
     }
+    if (getenv("LPB200_DEBUG")) {
+        // how well the dynamic queue balanced this launch: greedy list schedule of the measured item
+        // costs (objective evaluations) on `grid` CTA slots, ideal / makespan
+        std::vector<double> slot(grid, 0.0);
+        double total = 0.0;
+        unsigned longest = 0;
+        for (size_t it = 0; it < n_items; it++) {
+            size_t k = std::min_element(slot.begin(), slot.end()) - slot.begin();
+            slot[k] += evals[it];
+            total += evals[it];
+            longest = std::max(longest, evals[it]);
+        }
+        double makespan = *std::max_element(slot.begin(), slot.end());
+        fprintf(stderr, "[lpb200] fit_mudisp: %zu items, %.0f evaluations/item (max %u), kernel %.1f ms, queue balance %.3f\n",
+                n_items, total / n_items, longest, ms, total / grid / makespan);
+    }
     bool nonfinite = false;
     for (int i = 0; i < G; i++) {
         int best = 0;
