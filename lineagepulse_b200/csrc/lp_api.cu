@@ -49,6 +49,7 @@ struct lpb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int use_table = 1;
     int no_fastpath = 0;   // LPB200_NO_FASTPATH=1: always run the generic evaluator (testing)
+    int ctas_per_sm = LP_FAST_MINBLOCKS;  // persistent fit CTAs per SM (LPB200_CTAS_PER_SM overrides)
 };
 
 static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
@@ -180,6 +181,8 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
     }
     const char *e = getenv("LPB200_NO_TABLE");
     if (e && atoi(e)) c->use_table = 0;
+    e = getenv("LPB200_CTAS_PER_SM");
+    if (e && atoi(e) > 0) c->ctas_per_sm = atoi(e);
     e = getenv("LPB200_NO_FASTPATH");
     if (e && atoi(e)) c->no_fastpath = 1;
     return c;
@@ -739,7 +742,7 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
     CK(cudaMemcpyAsync(d_theta0.p, theta0.data(), sizeof(double) * theta0.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(d_queue.p, 0, sizeof(int), ctx->stream));
     const int threads = fit_threads(N);
-    const int grid = (int)std::min<size_t>(n_items, (size_t)ctx->sm_count * 4);
+    const int grid = (int)std::min<size_t>(n_items, (size_t)ctx->sm_count * ctx->ctas_per_sm);
     FitArgs A{};
     A.D = D;
     A.M = M;

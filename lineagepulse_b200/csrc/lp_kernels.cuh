@@ -21,7 +21,9 @@
 #include "lp_model.cuh"
 
 #define LP_KC 32          // evaluation points per chunk (one warp row)
+#ifndef LP_TAB
 #define LP_TAB 1024       // entries of one (x, phi) table
+#endif
 #define LP_NTAB 3         // tables per pass: base phi, phi + eps, phi - eps
 #define LP_MAX_WARPS 8
 #define LP_FIT_THREADS 256
