@@ -70,7 +70,8 @@ class Stats(C.Structure):
                 ("kernel_ms", C.c_double)]
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+F64, I64 = 0, 1
 
 
 def default_control() -> Control:

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -78,12 +79,14 @@ struct PoolBlock {
 };
 static std::vector<PoolBlock> g_pool;
 static size_t g_pool_bytes = 0;
+static std::mutex g_pool_mutex;   // contexts of several host threads share the pool
 static const size_t POOL_CAP_BYTES = (size_t)16 << 30;
 
 static cudaError_t pool_alloc(void **out, size_t bytes, size_t *got) {
     int dev = 0;
     cudaGetDevice(&dev);
     bytes = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    std::unique_lock<std::mutex> lock(g_pool_mutex);
     size_t best = (size_t)-1;
     for (size_t k = 0; k < g_pool.size(); k++)
         if (g_pool[k].device == dev && g_pool[k].bytes >= bytes && g_pool[k].bytes <= 2 * bytes + ((size_t)1 << 20) &&
@@ -96,20 +99,25 @@ static cudaError_t pool_alloc(void **out, size_t bytes, size_t *got) {
         g_pool.erase(g_pool.begin() + best);
         return cudaSuccess;
     }
+    lock.unlock();
     *got = bytes;
     return cudaMalloc(out, bytes);
 }
 static void pool_free(void *p, size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (g_pool_bytes + bytes > POOL_CAP_BYTES) {
-        cudaFree(p);
-        return;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (g_pool_bytes + bytes <= POOL_CAP_BYTES) {
+            g_pool.push_back(PoolBlock{p, bytes, dev});
+            g_pool_bytes += bytes;
+            return;
+        }
     }
-    g_pool.push_back(PoolBlock{p, bytes, dev});
-    g_pool_bytes += bytes;
+    cudaFree(p);
 }
 static void pool_release(int device) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
     for (size_t k = 0; k < g_pool.size();) {
         if (g_pool[k].device == device) {
             cudaFree(g_pool[k].p);
@@ -241,9 +249,9 @@ extern "C" int lpb200_reset_stats(lpb200_ctx *ctx) {
     return 0;
 }
 
-static int do_allreduce(lpb200_ctx *ctx, double *dev, size_t count) {
+static int do_allreduce(lpb200_ctx *ctx, void *dev, size_t count, int dtype) {
     if (ctx->world <= 1) return 0;
-    int rc = ctx->allreduce(ctx->allreduce_user, dev, count, (void *)ctx->stream);
+    int rc = ctx->allreduce(ctx->allreduce_user, dev, count, dtype, (void *)ctx->stream);
     if (rc != 0) return set_err(ctx, LPB200_E_COMM, "all-reduce callback failed (%d)", rc);
     return 0;
 }
@@ -251,7 +259,19 @@ static int do_allreduce(lpb200_ctx *ctx, double *dev, size_t count) {
 // ---------------------------------------------------------------------------------------------
 // data
 // ---------------------------------------------------------------------------------------------
-static int finish_counts(lpb200_ctx *ctx, int32_t *d_i32, int G, int N, size_t pitch) {
+// temporary int32 image of the count matrix: freed on every error path, released into the context
+// only when it becomes the resident copy
+struct TmpCounts {
+    int32_t *p = nullptr;
+    ~TmpCounts() { if (p) cudaFree(p); }
+    int32_t *release() { int32_t *q = p; p = nullptr; return q; }
+};
+
+static void free_design(lpb200_ctx *c);
+
+static int finish_counts(lpb200_ctx *ctx, TmpCounts &tmp, int G, int N, size_t pitch) {
+    int32_t *d_i32 = tmp.p;
+    free_design(ctx);  // a design belongs to one matrix shape
     // row statistics, then narrow to uint16 when every count fits
     DevBuf<double> d_mean;
     CK(d_mean.alloc(G));
@@ -284,11 +304,10 @@ static int finish_counts(lpb200_ctx *ctx, int32_t *d_i32, int G, int N, size_t p
         narrow_u16_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_i32, d16, (size_t)G * pitch);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(d_i32);
-        ctx->d_counts = d16;
+        ctx->d_counts = d16;   // tmp frees the int32 image
         ctx->is_u16 = true;
     } else {
-        ctx->d_counts = d_i32;
+        ctx->d_counts = tmp.release();
         ctx->is_u16 = false;
     }
     ctx->stats.launches += 3;
@@ -303,8 +322,9 @@ extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const dou
     if (G <= 0 || N <= 0 || !x) return set_err(ctx, LPB200_E_ARG, "load_counts_dense: bad arguments");
     CK(cudaSetDevice(ctx->device));
     size_t pitch = row_pitch(N);
-    int32_t *d_i32 = nullptr;
-    CK(cudaMalloc((void **)&d_i32, sizeof(int32_t) * (size_t)G * pitch));
+    TmpCounts tmp;
+    CK(cudaMalloc((void **)&tmp.p, sizeof(int32_t) * (size_t)G * pitch));
+    int32_t *d_i32 = tmp.p;
     CK(cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * (size_t)G * pitch, ctx->stream));
     // column slabs of the R matrix are contiguous: stream them through a bounded staging buffer
     size_t slab_cols = std::max<size_t>(1, std::min<size_t>(N, ((size_t)256 << 20) / (sizeof(double) * (size_t)G)));
@@ -318,7 +338,7 @@ extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const dou
         CK(cudaGetLastError());
         ctx->stats.launches++;
     }
-    return finish_counts(ctx, d_i32, G, N, pitch);
+    return finish_counts(ctx, tmp, G, N, pitch);
 }
 
 extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32_t *p, const int32_t *i, const double *x) {
@@ -327,8 +347,9 @@ extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32
     CK(cudaSetDevice(ctx->device));
     size_t nnz = (size_t)p[N];
     size_t pitch = row_pitch(N);
-    int32_t *d_i32 = nullptr;
-    CK(cudaMalloc((void **)&d_i32, sizeof(int32_t) * (size_t)G * pitch));
+    TmpCounts tmp;
+    CK(cudaMalloc((void **)&tmp.p, sizeof(int32_t) * (size_t)G * pitch));
+    int32_t *d_i32 = tmp.p;
     CK(cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * (size_t)G * pitch, ctx->stream));
     DevBuf<int32_t> dp, di;
     DevBuf<double> dx;
@@ -343,7 +364,7 @@ extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32
     scatter_csc_kernel<<<N, 128, 0, ctx->stream>>>(dp.p, di.p, dx.p, N, d_i32, pitch);
     CK(cudaGetLastError());
     ctx->stats.launches++;
-    return finish_counts(ctx, d_i32, G, N, pitch);
+    return finish_counts(ctx, tmp, G, N, pitch);
 }
 
 extern "C" int lpb200_load_counts_i32(lpb200_ctx *ctx, int G, int N, const int32_t *x, int is_device) {
@@ -351,12 +372,13 @@ extern "C" int lpb200_load_counts_i32(lpb200_ctx *ctx, int G, int N, const int32
     if (G <= 0 || N <= 0 || !x) return set_err(ctx, LPB200_E_ARG, "load_counts_i32: bad arguments");
     CK(cudaSetDevice(ctx->device));
     size_t pitch = row_pitch(N);
-    int32_t *d_i32 = nullptr;
-    CK(cudaMalloc((void **)&d_i32, sizeof(int32_t) * (size_t)G * pitch));
+    TmpCounts tmp;
+    CK(cudaMalloc((void **)&tmp.p, sizeof(int32_t) * (size_t)G * pitch));
+    int32_t *d_i32 = tmp.p;
     CK(cudaMemsetAsync(d_i32, 0, sizeof(int32_t) * (size_t)G * pitch, ctx->stream));
     CK(cudaMemcpy2DAsync(d_i32, pitch * sizeof(int32_t), x, (size_t)N * sizeof(int32_t), (size_t)N * sizeof(int32_t), G,
                          is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    return finish_counts(ctx, d_i32, G, N, pitch);
+    return finish_counts(ctx, tmp, G, N, pitch);
 }
 
 extern "C" int lpb200_row_means(lpb200_ctx *ctx, double *means) {
@@ -891,18 +913,21 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     if (!p->mat_drop) return set_err(ctx, LPB200_E_ARG, "mat_drop is NULL");
     std::vector<double> nat;
     params_to_nat(ctx, M, p, nat);
-    DevBuf<double> d_nat, d_drop, d_partial, d_vals, d_ll, d_total;
+    DevBuf<double> d_nat, d_drop, d_vals, d_ll, d_total;
+    DevBuf<long long> d_partial, d_vals_i;
     DevBuf<PiState> d_states;
     DevBuf<int> d_active, d_conv;
     DevBuf<unsigned> d_evals;
     const int cell_blocks = (N + 127) / 128;
     int n_chunks = std::max(1, std::min(64, (ctx->sm_count * 4 + cell_blocks - 1) / cell_blocks));
     n_chunks = std::min(n_chunks, G);
-    const int gpc = (G + n_chunks - 1) / n_chunks;
+    int gpc = (G + n_chunks - 1) / n_chunks;
+    gpc = (gpc + LP_PI_BLOCK - 1) / LP_PI_BLOCK * LP_PI_BLOCK;   // chunks start on summation-block boundaries
     n_chunks = (G + gpc - 1) / gpc;
     CK(d_nat.alloc(nat.size()));
     CK(d_drop.alloc((size_t)N * q));
-    CK(d_partial.alloc((size_t)n_chunks * LP_PI_KP * N));
+    CK(d_partial.alloc((size_t)3 * n_chunks * LP_PI_KP * N));
+    CK(d_vals_i.alloc((size_t)3 * LP_PI_KP * N));
     CK(d_vals.alloc((size_t)LP_PI_KP * N));
     CK(d_states.alloc(N));
     CK(d_active.alloc(1));
@@ -915,7 +940,8 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     A.C = count_view(ctx);
     A.nat = d_nat.p;
     A.states = d_states.p;
-    A.partial = d_partial.p;
+    A.partial_i = d_partial.p;
+    A.vals_i = d_vals_i.p;
     A.vals = d_vals.p;
     A.genes_per_chunk = gpc;
     A.n_chunks = n_chunks;
@@ -944,10 +970,12 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
             CK(cudaGetLastError());
             pi_reduce_kernel<<<nb, 128, 0, ctx->stream>>>(A);
             CK(cudaGetLastError());
-            if ((rc = do_allreduce(ctx, d_vals.p, (size_t)LP_PI_KP * N))) return rc;
+            if ((rc = do_allreduce(ctx, d_vals_i.p, (size_t)3 * LP_PI_KP * N, LPB200_I64))) return rc;
+            pi_combine_kernel<<<nb, 128, 0, ctx->stream>>>(A);
+            CK(cudaGetLastError());
             pi_advance_kernel<<<nb, 128, 0, ctx->stream>>>(A);
             CK(cudaGetLastError());
-            ctx->stats.launches += 3;
+            ctx->stats.launches += 4;
             if (++since_check < check_every) continue;
             since_check = 0;
             int active = 0;
@@ -1014,10 +1042,12 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
         CK(cudaGetLastError());
         pi_reduce_kernel<<<nb, 128, 0, ctx->stream>>>(A);
         CK(cudaGetLastError());
-        pi_total_kernel<<<nk, 256, 0, ctx->stream>>>(d_vals.p, N, d_total.p);
+        if ((rc = do_allreduce(ctx, d_vals_i.p, (size_t)3 * LP_PI_KP * N, LPB200_I64))) return rc;
+        pi_combine_kernel<<<nb, 128, 0, ctx->stream>>>(A);
         CK(cudaGetLastError());
-        ctx->stats.launches += 3;
-        if ((rc = do_allreduce(ctx, d_total.p, (size_t)nk))) return rc;
+        pi_total_kernel<<<nk, 256, 0, ctx->stream>>>(d_vals.p, N, d_total.p);   // every shard sums the same cells in the same order
+        CK(cudaGetLastError());
+        ctx->stats.launches += 4;
         CK(cudaMemcpyAsync(vals, d_total.p, sizeof(double) * nk, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->stats.fn_evals += (uint64_t)nk;
@@ -1136,18 +1166,20 @@ extern "C" int lpb200_init_params(lpb200_ctx *ctx, const lpb200_model *m, lpb200
 // ---------------------------------------------------------------------------------------------
 // fitModel: the EM / coordinate-ascent loop (fitModel.R:137-356)
 // ---------------------------------------------------------------------------------------------
+// sum(vecLL) over all genes of all shards (fitModel.R:328): exact fixed-point accumulation, so every
+// shard count gives the same scalar and the EM stopping rule takes the same decision
 static int sum_ll(lpb200_ctx *ctx, const double *ll, int G, double *out) {
-    long double s = 0.0L;
-    for (int i = 0; i < G; i++) s += ll[i];
-    double v = (double)s;
-    if (ctx->world > 1) {  // sum over the gene shards
-        CK(cudaMemcpyAsync(ctx->d_xchg, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        int rc = do_allreduce(ctx, ctx->d_xchg, 1);
+    ExactSum s = {0, 0, 0};
+    for (int i = 0; i < G; i++) lp_exact_add(s, ll[i]);
+    long long w[3] = {s.a, s.b, s.bad};
+    if (ctx->world > 1) {
+        CK(cudaMemcpyAsync(ctx->d_xchg, w, sizeof(w), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = do_allreduce(ctx, ctx->d_xchg, 3, LPB200_I64);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(&v, ctx->d_xchg, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(w, ctx->d_xchg, sizeof(w), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    *out = v;
+    *out = lp_exact_value(w[0], w[1], w[2]);
     return 0;
 }
 
@@ -1184,7 +1216,7 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
     if (ctx->world > 1) {  // all(vecMuDispEstConverged == 0) over every shard
         double v = any_nonconv;
         CK(cudaMemcpyAsync(ctx->d_xchg, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        if ((rc = do_allreduce(ctx, ctx->d_xchg, 1))) return rc;
+        if ((rc = do_allreduce(ctx, ctx->d_xchg, 1, LPB200_F64))) return rc;
         CK(cudaMemcpyAsync(&v, ctx->d_xchg, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         any_nonconv = v > 0;

@@ -36,6 +36,33 @@
 #define LP_GENERIC_MINBLOCKS 4
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// Exact, order-independent summation of the cross-shard quantities.  A double v (|v| < 2^62) is split
+// into two integers a = trunc(v 2^20), b = trunc((v 2^20 - a) 2^40), i.e. v = a 2^-20 + b 2^-60 up to
+// 2^-60 truncation.  Sums of the a's and b's are plain int64 additions -- associative, so the result
+// does not depend on the gene sharding, the chunking or the all-reduce order -- and the total is
+// converted back once.  Non-finite inputs are counted in a third word and poison the result.
+// ---------------------------------------------------------------------------------------------
+#define LP_PI_BLOCK 16   // genes per fixed summation block (shards and chunks start at multiples of this)
+struct ExactSum {
+    long long a, b, bad;
+};
+LP_HD void lp_exact_add(ExactSum &s, double v) {
+    if (!(fabs(v) < 4.0e18)) {   // NaN / Inf / out of range
+        s.bad += 1;
+        return;
+    }
+    const double scaled = v * 1048576.0;            // 2^20, exact
+    const double ai = trunc(scaled);
+    const double r = scaled - ai;                   // exact, |r| < 1
+    s.a += (long long)ai;
+    s.b += (long long)trunc(r * 1099511627776.0);   // 2^40
+}
+LP_HD double lp_exact_value(long long a, long long b, long long bad) {
+    if (bad != 0) return NAN;
+    return (double)a * 9.5367431640625e-07 + (double)b * 8.6736173798840355e-19;   // 2^-20, 2^-60
+}
+
 __device__ __forceinline__ int lp_load_count(const uint16_t *r, int j) {
     unsigned v = r[j];
     return v == LP_NA_U16 ? -1 : (int)v;
@@ -517,7 +544,8 @@ struct PiArgs {
     CountView C;
     const double *nat;      // [G][n_nat] natural-scale gene parameters
     PiState *states;        // [N]
-    double *partial;        // [n_chunks][LP_PI_KP][N]
+    long long *partial_i;   // [3][n_chunks][LP_PI_KP][N]: exact (a, b, bad) sums of the chunk's 16-gene blocks
+    long long *vals_i;      // [3][LP_PI_KP][N]: exact (a, b, bad) sums over blocks -- the all-reduced block
     double *vals;           // [LP_PI_KP][N]
     int genes_per_chunk, n_chunks;
     int shared_nk;          // > 0: ForAllCells, every cell evaluates shared_theta[0..shared_nk)
@@ -535,7 +563,7 @@ LP_HD void lp_pi_transform(int drop_model, int q, const double *th, double *lin)
         if (lin[1] > -LP_CLAMP_LO) lin[1] = -LP_CLAMP_LO;
 }
 
-#define LP_PI_TILE 8   // genes staged in shared memory per step
+#define LP_PI_TILE LP_PI_BLOCK   // genes staged in shared memory per step = one summation block
 template <typename CT>
 __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ PiArgs A) {
     __shared__ PointNat sg[LP_PI_TILE];
@@ -569,9 +597,14 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
             }
         }
     }
+    // a block of LP_PI_BLOCK genes is summed in gene order in double; blocks are combined exactly
+    ExactSum ex[LP_PI_KP];
     double acc[LP_PI_KP];
 #pragma unroll
-    for (int k = 0; k < LP_PI_KP; k++) acc[k] = 0.0;
+    for (int k = 0; k < LP_PI_KP; k++) {
+        acc[k] = 0.0;
+        ex[k].a = ex[k].b = ex[k].bad = 0;
+    }
     const double s = (j < D.N && D.sf) ? D.sf[j] : 1.0;
     const CT *base = reinterpret_cast<const CT *>(A.C.ptr);
 
@@ -608,15 +641,29 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < LP_PI_KP; k++) {
+            if (k < nk) {
+                lp_exact_add(ex[k], acc[k]);
+                acc[k] = 0.0;
+            }
+        }
     }
     if (j < D.N) {
+        const size_t plane = (size_t)A.n_chunks * LP_PI_KP * D.N;
 #pragma unroll
-        for (int k = 0; k < LP_PI_KP; k++)
-            if (k < nk) A.partial[((size_t)blockIdx.y * LP_PI_KP + k) * D.N + j] = acc[k];
+        for (int k = 0; k < LP_PI_KP; k++) {
+            if (k < nk) {
+                const size_t o = ((size_t)blockIdx.y * LP_PI_KP + k) * D.N + j;
+                A.partial_i[o] = ex[k].a;
+                A.partial_i[plane + o] = ex[k].b;
+                A.partial_i[2 * plane + o] = ex[k].bad;
+            }
+        }
     }
 }
 
-// vals[k][j] = sum over gene chunks (fixed order)
+// vals_i[.][k][j] = integer sum over this shard's gene chunks
 __global__ void pi_reduce_kernel(PiArgs A) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= A.D.N) return;
@@ -626,11 +673,33 @@ __global__ void pi_reduce_kernel(PiArgs A) {
         int req = A.states[j].req;
         nk = (req == LP_REQ_F) ? 1 : (req == LP_REQ_GRAD ? 2 * A.M.q_drop : 0);
     }
+    const size_t plane = (size_t)LP_PI_KP * A.D.N;
     for (int k = 0; k < LP_PI_KP; k++) {
-        double s = 0.0;
-        if (k < nk)
-            for (int c = 0; c < A.n_chunks; c++) s += A.partial[((size_t)c * LP_PI_KP + k) * A.D.N + j];
-        A.vals[(size_t)k * A.D.N + j] = s;   // inactive slots are written as 0 so the all-reduce is well defined
+        ExactSum s = {0, 0, 0};
+        if (k < nk) {
+            const size_t cplane = (size_t)A.n_chunks * LP_PI_KP * A.D.N;
+            for (int c = 0; c < A.n_chunks; c++) {
+                const size_t oc = ((size_t)c * LP_PI_KP + k) * A.D.N + j;
+                s.a += A.partial_i[oc];
+                s.b += A.partial_i[cplane + oc];
+                s.bad += A.partial_i[2 * cplane + oc];
+            }
+        }
+        const size_t o = (size_t)k * A.D.N + j;   // inactive slots are written as 0 so the all-reduce is well defined
+        A.vals_i[o] = s.a;
+        A.vals_i[plane + o] = s.b;
+        A.vals_i[2 * plane + o] = s.bad;
+    }
+}
+
+// after the all-reduce: back to doubles
+__global__ void pi_combine_kernel(PiArgs A) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.D.N) return;
+    const size_t plane = (size_t)LP_PI_KP * A.D.N;
+    for (int k = 0; k < LP_PI_KP; k++) {
+        const size_t o = (size_t)k * A.D.N + j;
+        A.vals[o] = lp_exact_value(A.vals_i[o], A.vals_i[plane + o], A.vals_i[2 * plane + o]);
     }
 }
 
@@ -682,14 +751,14 @@ __global__ void pi_compact_kernel(PiArgs A, int *list, int *count) {
 template <typename CT>
 __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ PiArgs A, const int *list) {
     __shared__ double s_vals[LP_PI_KP];
-    __shared__ double s_red[LP_PI_KP * 8];
+    __shared__ long long s_ex[LP_PI_KP][3];
     __shared__ double s_coef[LP_PI_KP][LP_PI_NP];
     __shared__ int s_nk;
     const DevDesign &D = A.D;
     const DevModel &M = A.M;
     const int j = list[blockIdx.x];
     const int q = M.q_drop, n_nat = lp_n_nat(M);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x;
     PiState &st = A.states[j];
     const double s = D.sf ? D.sf[j] : 1.0;
     const CT *base = reinterpret_cast<const CT *>(A.C.ptr);
@@ -711,48 +780,60 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
         __syncthreads();
         const int nk = s_nk;
         if (nk == 0) break;
-        double acc[LP_PI_KP];
+        // same summation structure as the lock-step path: 16-gene blocks summed in gene order, blocks
+        // combined exactly (shared-memory integer atomics), so a cell finished here gets the bits it
+        // would have got in lock-step rounds on any number of GPUs
+        if (tid < LP_PI_KP) {
+            s_ex[tid][0] = 0;
+            s_ex[tid][1] = 0;
+            s_ex[tid][2] = 0;
+        }
+        __syncthreads();
+        const int n_blocks = (D.G + LP_PI_BLOCK - 1) / LP_PI_BLOCK;
+        for (int blk = tid; blk < n_blocks; blk += blockDim.x) {
+            double acc[LP_PI_KP];
 #pragma unroll
-        for (int k = 0; k < LP_PI_KP; k++) acc[k] = 0.0;
-        for (int i = tid; i < D.G; i += blockDim.x) {
-            const int x = lp_load_count(base + (size_t)i * A.C.pitch, j);
-            if (x < 0) continue;
-            PointNat P;
-            lp_nat_load(M, A.nat + (size_t)i * n_nat, P);
-            const double mu = lp_mu_at(D, M, P, j);
-            const double phi = lp_disp_at(D, M, P, j);
-            const double mus = mu * s;
-            const double lmu = (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) ? log(mu) : 0.0;
-            double core;
-            if (x == 0) core = exp(phi * log(phi / (phi + mus)));
-            else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
+            for (int k = 0; k < LP_PI_KP; k++) acc[k] = 0.0;
+            const int i1 = min(D.G, (blk + 1) * LP_PI_BLOCK);
+            for (int i = blk * LP_PI_BLOCK; i < i1; i++) {
+                const int x = lp_load_count(base + (size_t)i * A.C.pitch, j);
+                if (x < 0) continue;
+                PointNat P;
+                lp_nat_load(M, A.nat + (size_t)i * n_nat, P);
+                const double mu = lp_mu_at(D, M, P, j);
+                const double phi = lp_disp_at(D, M, P, j);
+                const double mus = mu * s;
+                const double lmu = (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) ? log(mu) : 0.0;
+                double core;
+                if (x == 0) core = exp(phi * log(phi / (phi + mus)));
+                else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
+#pragma unroll
+                for (int k = 0; k < LP_PI_KP; k++) {
+                    if (k < nk) {
+                        int u = 1;
+                        double lin = 1.0 * s_coef[k][0];
+                        if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * s_coef[k][u++];
+                        for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * s_coef[k][u];
+                        double pi = lp_dropout_rate(lin);
+                        double v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
+                        if (v < LP_LL_FLOOR) v = LP_LL_FLOOR;
+                        acc[k] += v;
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < LP_PI_KP; k++) {
                 if (k < nk) {
-                    int u = 1;
-                    double lin = 1.0 * s_coef[k][0];
-                    if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * s_coef[k][u++];
-                    for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * s_coef[k][u];
-                    double pi = lp_dropout_rate(lin);
-                    double v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
-                    if (v < LP_LL_FLOOR) v = LP_LL_FLOOR;
-                    acc[k] += v;
+                    ExactSum e = {0, 0, 0};
+                    lp_exact_add(e, acc[k]);
+                    atomicAdd((unsigned long long *)&s_ex[k][0], (unsigned long long)e.a);
+                    atomicAdd((unsigned long long *)&s_ex[k][1], (unsigned long long)e.b);
+                    if (e.bad) atomicAdd((unsigned long long *)&s_ex[k][2], 1ull);
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < LP_PI_KP; k++) {
-            if (k < nk) {
-                double v = lp_warp_sum(acc[k]);
-                if (lane == 0) s_red[k * 8 + warp] = v;
-            }
-        }
         __syncthreads();
-        if (tid < nk) {
-            double v = 0.0;
-            for (int w = 0; w < nwarps; w++) v += s_red[tid * 8 + w];
-            s_vals[tid] = v;
-        }
+        if (tid < nk) s_vals[tid] = lp_exact_value(s_ex[tid][0], s_ex[tid][1], s_ex[tid][2]);
         __syncthreads();
         if (tid == 0) bfgs_advance(st, s_vals);
         __syncthreads();

@@ -12,21 +12,26 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_bounds(n_genes: int, world: int):
-    """Contiguous gene blocks, sizes differing by at most one."""
-    base, extra = divmod(n_genes, world)
+SUM_BLOCK = 16  # LP_PI_BLOCK: shards start on summation-block boundaries => results independent of the shard count
+
+
+def shard_bounds(n_genes: int, world: int, align: int = SUM_BLOCK):
+    """Contiguous gene ranges of near-equal size whose starts are multiples of ``align``."""
+    n_blocks = (n_genes + align - 1) // align
+    base, extra = divmod(n_blocks, world)
     bounds = [0]
     for r in range(world):
-        bounds.append(bounds[-1] + base + (1 if r < extra else 0))
+        bounds.append(min(n_genes, bounds[-1] + (base + (1 if r < extra else 0)) * align))
+    bounds[-1] = n_genes
     return bounds
 
 
-class _CudaF64View:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__."""
+class _CudaWordView:
+    """Exposes a raw device pointer (8-byte words) to torch through __cuda_array_interface__."""
 
-    def __init__(self, ptr: int, count: int):
-        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False),
-                                         "version": 3, "strides": None}
+    def __init__(self, ptr: int, count: int, dtype: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8" if dtype == 1 else "<f8",
+                                         "data": (ptr, False), "version": 3, "strides": None}
 
 
 def make_allreduce(group=None):
@@ -34,8 +39,8 @@ def make_allreduce(group=None):
     import torch
     import torch.distributed as dist
 
-    def allreduce(ptr: int, count: int, stream: int):
-        t = torch.as_tensor(_CudaF64View(ptr, count), device="cuda")
+    def allreduce(ptr: int, count: int, dtype: int, stream: int):
+        t = torch.as_tensor(_CudaWordView(ptr, count, dtype), device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
     return allreduce

@@ -54,11 +54,12 @@ class Engine:
         self._check(self.lib.lpb200_set_stream(self.ctx, C.c_void_p(cuda_stream)))
 
     def set_collective(self, rank: int, world: int, allreduce):
-        """``allreduce(dev_ptr: int, count: int, stream: int) -> None`` sums ``count`` doubles
-        in place across the gene shards (e.g. torch.distributed.all_reduce over NCCL)."""
-        def _cb(user, ptr, count, stream):
+        """``allreduce(dev_ptr: int, count: int, dtype: int, stream: int) -> None`` sums ``count``
+        8-byte words (dtype _cabi.F64 or _cabi.I64) in place across the gene shards (e.g.
+        torch.distributed.all_reduce over NCCL)."""
+        def _cb(user, ptr, count, dtype, stream):
             try:
-                allreduce(int(ptr), int(count), int(stream or 0))
+                allreduce(int(ptr), int(count), int(dtype), int(stream or 0))
                 return 0
             except Exception:  # never let an exception cross the C boundary
                 import traceback

@@ -82,5 +82,9 @@ def test_gene_sharded_exchanges_world2():
 
 def test_shard_bounds():
     from lineagepulse_b200.distributed import shard_bounds
-    assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
-    assert shard_bounds(20000, 8)[-1] == 20000 and len(shard_bounds(20000, 8)) == 9
+    assert shard_bounds(10, 4, align=1) == [0, 3, 6, 8, 10]
+    b = shard_bounds(20000, 8)
+    assert b[0] == 0 and b[-1] == 20000 and len(b) == 9
+    assert all(x % 16 == 0 for x in b[:-1])          # shards start on summation-block boundaries
+    assert max(np.diff(b)) - min(np.diff(b)) <= 16
+    assert shard_bounds(10, 4) == [0, 10, 10, 10, 10]  # fewer blocks than shards: trailing shards are empty
