@@ -124,13 +124,17 @@ def native_pipeline(eng, design, A, min_rowmean):
 
     pA = A.ParamsData(design, mA)
     run("A", mA, pA, True)
+    # fits B, C, D are independent given A's drop-out model: one concurrent call (lpb200_fit_model_multi)
     pB = A.ParamsData(design, mB)
     pB.mat_drop = pA.mat_drop.copy(order="F")
-    run("B", mB, pB, False)
     pC = A.ParamsData(design, mC)
-    run("C", mC, pC, False)
     pD = A.ParamsData(design, mD)
-    run("D", mD, pD, False)
+    eng.reset_stats()
+    res = eng.fit_model_multi([(mB, pB), (mC, pC), (mD, pD)], ctl, min_rowmean)
+    st = eng.stats()
+    for tag, r in zip("BCD", res):
+        work[tag] = {"fn_evals": 0, "ole": r["ole"], "launches": 0, "kernel_ms": 0.0}
+    work["BCD"] = st
     eng.reset_stats()
     llf, llr = eng.eval_loglik(mB, pB), eng.eval_loglik(mA, pA)
     llf_nb, llr_nb = eng.eval_loglik(mD, pD), eng.eval_loglik(mC, pC)
@@ -344,9 +348,10 @@ def main():
     # ---- roofline of the dominant kernel (fit_mudisp_kernel on the impulse fits B and D) --------
     w = works[-1]
     flop_B = w["B"]["ole"] * flops_per_ole(True, True, zero_frac)
+    flop_C = w["C"]["ole"] * flops_per_ole(False, False, zero_frac)
     flop_D = w["D"]["ole"] * flops_per_ole(True, False, zero_frac)
-    ker_s = (w["B"]["kernel_ms"] + w["D"]["kernel_ms"]) / 1e3
-    achieved = (flop_B + flop_D) / ker_s / 1e12
+    ker_s = w["BCD"]["kernel_ms"] / 1e3   # span of the three overlapping fit_mudisp launches
+    achieved = (flop_B + flop_C + flop_D) / ker_s / 1e12
     share = ker_s * 1e3 / step_ms[-1]
     ct_bytes = 2 if int(X.max()) < 65535 else 4   # the library stores uint16 unless a count needs int32
     ct_name = "uint16_t" if ct_bytes == 2 else "int32_t"
@@ -358,9 +363,9 @@ def main():
                 # (82.7 MB at 1 184 genes x 10 000 cells, u16 counts), scaled to this launch's matrix
                 "traffic": 82.65e6 * (G * N) / (1184.0 * 10000.0) * ((ct_bytes + 4.0) / 6.0),
                 "traffic_unit": "bytes per launch (ncu, scaled by matrix size)",
-                "kernel": f"fit_mudisp_kernel<{ct_name}, impulse> (fits B + D)",
+                "kernel": f"fit_mudisp_kernel<{ct_name}> (fits B, C, D: three overlapping launches)",
                 "kernel_share_of_step": share,
-                "ole_per_s": (w["B"]["ole"] + w["D"]["ole"]) / ker_s,
+                "ole_per_s": (w["B"]["ole"] + w["C"]["ole"] + w["D"]["ole"]) / ker_s,
                 "peak_source": "FP64 DFMA chain probe measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "hbm": {"algorithmic_bytes_per_launch": count_bytes + perm_bytes,
                         "achieved_GBps": 2 * (count_bytes + perm_bytes) / ker_s / 1e9,

@@ -10,6 +10,6 @@ from .splines import ns  # noqa: F401
 from .simulate import simulateContinuousDataSet  # noqa: F401
 from .api import (  # noqa: F401
     CountMatrix, LineagePulseObject, LineagePulseError, runLineagePulse, processSCData, calcNormConst,
-    fitLPModels, fitModel, fitMuDisp, fitPi, evalLogLikMatrix, runDEAnalysis, testDropout,
+    fitLPModels, fitModel, fitModelsConcurrently, fitMuDisp, fitPi, evalLogLikMatrix, runDEAnalysis, testDropout,
     calcPostDrop_Matrix, getPostDrop, getNormData, getFitsMean, getFitsDispersion, getFitsDropout,
     writeReport)

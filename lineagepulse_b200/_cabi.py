@@ -289,6 +289,8 @@ def declare_product_prototypes(lib):
         "lpb200_fit_pi": (C.c_int, [vp, P(Model), P(Params), P(Control), c_double_p, c_int32_p]),
         "lpb200_fit_model": (C.c_int, [vp, P(Model), P(Params), C.c_int, P(Control), C.c_double,
                                        c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_int32_p]),
+        "lpb200_fit_model_multi": (C.c_int, [vp, C.c_int, P(Model), P(Params), P(Control), C.c_double, c_double_p,
+                                             c_double_p, c_int32_p, c_double_p, c_int32_p, P(C.c_uint64)]),
         "lpb200_post_drop": (C.c_int, [vp, P(Model), P(Params), c_int32_p, C.c_int, c_double_p]),
         "lpb200_expand_fits": (C.c_int, [vp, P(Model), P(Params), c_int32_p, C.c_int, C.c_int, c_double_p]),
         "lpb200_lrt": (C.c_int, [c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),

@@ -371,6 +371,75 @@ def fitModel(matCounts, dfAnnotation, vecConfoundersMu=None, vecConfoundersDisp=
     r = eng.fit_model(model, p, boolFitDrop, ctl, min_rowmean_global)
     dt = time.time() - t0
     _fill_models(design, model, p, lsMu, lsDisp, lsDrop, fill_drop=boolFitDrop)
+    return _fit_result(lsMu, lsDisp, lsDrop, r, ctl.max_cycles if boolFitDrop else 1, dt, boolVerbose)
+
+
+def _union(*vals):
+    for v in vals:
+        if v is not None:
+            return v
+    return None
+
+
+def fitModelsConcurrently(matCounts, dfAnnotation, lsSpecs, vecConfoundersMu=None, vecConfoundersDisp=None,
+                          vecNormConst=None, scaDFSplinesMu=None, scaDFSplinesDisp=None, boolVerbose=True,
+                          min_rowmean_global=float("nan")):
+    """Several fitModel() calls that do not estimate the drop-out model (fits B, C, D of fitLPModels,
+    fitWrapperLP.R:152-238) in one library call: identical results to sequential fitModel() calls, but
+    the fit kernels overlap on the GPU (lpb200_fit_model_multi).  ``lsSpecs`` = list of dicts with
+    strMuModel, strDispModel, strDropModel and (unless "none") lsDropModel."""
+    counts = _as_counts(matCounts)
+    G, N = counts.shape
+    if vecNormConst is None:
+        vecNormConst = np.ones(N)
+    ctl = A.default_control()
+    built = []
+    for spec in lsSpecs:
+        if spec["strMuModel"] == "MM":
+            raise LineagePulseError("LineagePulse ERROR: fitMMZINB() not yet supported. Contact developer.")
+        lsDropModel = spec.get("lsDropModel")
+        strDrop = spec.get("strDropModel", "none")
+        if strDrop != "none" and lsDropModel is None:
+            raise LineagePulseError("fitModelsConcurrently(): a drop-out model must be supplied (use fitModel() to estimate it)")
+        lsMu, lsDisp, lsDropNew = _global_models(
+            counts, dfAnnotation, vecConfoundersMu, vecConfoundersDisp, vecNormConst, scaDFSplinesMu, scaDFSplinesDisp,
+            spec["strMuModel"], spec["strDispModel"], strDrop, spec.get("strDropFitGroup", "PerCell"), None,
+            ctl.maxit_mudisp, ctl.reltol_mudisp, ctl.maxit_pi, ctl.reltol_pi)
+        built.append((lsMu, lsDisp, lsDropModel if lsDropModel is not None else lsDropNew))
+    # one design holding every covariate any of the models needs
+    gms = [b[0]["lsMuModelGlobal"] for b in built]
+    gds = [b[1]["lsDispModelGlobal"] for b in built]
+    t = _union(*[g.get("vecContinuousCovar") for g in gms])
+    need_impulse = any(g["strMuModel"] == "impulse" for g in gms)
+    design = A.DesignData(
+        G, N, size_factors=vecNormConst, pseudotime=t,
+        groups=_union(*[g.get("vecidxGroups") for g in gms + gds]),
+        spline_basis_mu=_union(*[g.get("matSplineBasis") for g in gms]),
+        spline_basis_disp=_union(*[g.get("matSplineBasis") for g in gds]),
+        impulse_basis=ns(t, 4, intercept=True) if need_impulse else None,
+        confounders_mu=_union(*[g.get("lsvecidxBatchAssign") for g in gms]),
+        confounders_disp=_union(*[g.get("lsvecidxBatchAssign") for g in gds]),
+        pi_const_pred=_union(*[(b[2] or {}).get("matPiConstPredictors") for b in built]))
+    eng = counts.engine()
+    eng.set_design(design)
+    jobs = []
+    for lsMu, lsDisp, lsDrop in built:
+        model = _model_struct(lsMu, lsDisp, lsDrop)
+        p = A.ParamsData(design, model)
+        if model.drop_model != A.DROP_NONE:
+            p.mat_drop = np.asfortranarray(lsDrop["matDropoutLinModel"], dtype=np.float64)
+        jobs.append((model, p))
+    t0 = time.time()
+    res = eng.fit_model_multi(jobs, ctl, min_rowmean_global)
+    dt = time.time() - t0
+    out = []
+    for (lsMu, lsDisp, lsDrop), (model, p), r in zip(built, jobs, res):
+        _fill_models(design, model, p, lsMu, lsDisp, lsDrop, fill_drop=False)
+        out.append(_fit_result(lsMu, lsDisp, lsDrop, r, 1, dt / len(jobs), boolVerbose))
+    return out
+
+
+def _fit_result(lsMu, lsDisp, lsDrop, r, ncyc, dt, boolVerbose):
     strReport = f"#  .   Initialisation: ll {r['ll_init']}\n"
     for k in range(r["n_iter"]):
         strReport += f"# {k + 1}.  Iteration with ll   {r['em_ll'][k]}\n"
@@ -380,7 +449,6 @@ def fitModel(matCounts, dfAnnotation, vecConfoundersMu=None, vecConfoundersDisp=
         strReport += f"(Mean-) Dispersion estimation did not converge in {n_bad} cases [codes: {codes}].\n"
     if boolVerbose:
         message(strReport.rstrip("\n"))
-    ncyc = ctl.max_cycles if boolFitDrop else 1
     return {"lsMuModel": lsMu, "lsDispModel": lsDisp, "lsDropModel": lsDrop,
             "boolConvergenceModel": r["converged"], "vecEMLogLikModel": r["em_ll"][:ncyc],
             "strReport": strReport, "vecLL": r["ll"], "vecConvergence": r["conv"], "scaTime": dt}
@@ -549,20 +617,23 @@ def fitLPModels(objLP, matPiConstPredictors=None, strMuModel="constant", strDisp
     objLP.strReport += fitA["strReport"]
     log(f"Finished fitting zero-inflated negative binomial model A with noise model in {round(fitA['scaTime'] / 60, 2)} min.")
     lsDropModelA = fitA["lsDropModel"]
+    # b) - d): the three remaining fits are independent of each other (fitWrapperLP.R:152-238); the
+    # reference runs them one after the other, here their kernels overlap on the GPU
     log(f"### b) Fit ZINB model B ({nameB}).")
-    fitB = fitModel(lsDropModel=lsDropModelA, strMuModel=strMuModelB, strDispModel=strDispModelB,
-                    strDropModel=strDropModel, strDropFitGroup=strDropFitGroup,
-                    matPiConstPredictors=matPiConstPredictors, **common)
-    objLP.strReport += fitB["strReport"]
-    log(f"Finished fitting zero-inflated negative binomial model B in {round(fitB['scaTime'] / 60, 2)} min.")
     log(f"### c) Fit NB model A ({nameA}).")
-    fitA_NB = fitModel(lsDropModel=None, strMuModel=strMuModelA, strDispModel=strDispModelA, strDropModel="none", **common)
-    objLP.strReport += fitA_NB["strReport"]
-    log(f"Finished fitting NB model B in {round(fitA_NB['scaTime'] / 60, 2)} min.")
     log(f"### d) Fit NB model B ({nameB}).")
-    fitB_NB = fitModel(lsDropModel=None, strMuModel=strMuModelB, strDispModel=strDispModelB, strDropModel="none", **common)
-    objLP.strReport += fitB_NB["strReport"]
-    log(f"Finished fitting NB model B in {round(fitB_NB['scaTime'] / 60, 2)} min.")
+    fitB, fitA_NB, fitB_NB = fitModelsConcurrently(
+        objLP.matCountsProc, objLP.dfAnnotationProc,
+        [dict(strMuModel=strMuModelB, strDispModel=strDispModelB, strDropModel=strDropModel,
+              strDropFitGroup=strDropFitGroup, lsDropModel=lsDropModelA),
+         dict(strMuModel=strMuModelA, strDispModel=strDispModelA, strDropModel="none"),
+         dict(strMuModel=strMuModelB, strDispModel=strDispModelB, strDropModel="none")],
+        vecConfoundersMu=objLP.vecConfoundersMu, vecConfoundersDisp=objLP.vecConfoundersDisp,
+        vecNormConst=objLP.vecNormConst, scaDFSplinesMu=objLP.scaDFSplinesMu,
+        scaDFSplinesDisp=objLP.scaDFSplinesDisp, boolVerbose=boolVerbose, min_rowmean_global=min_rowmean_global)
+    for fit, what in ((fitB, "zero-inflated negative binomial model B"), (fitA_NB, "NB model B"), (fitB_NB, "NB model B")):
+        objLP.strReport += fit["strReport"]
+        log(f"Finished fitting {what} in {round(fit['scaTime'] / 60, 2)} min.")
     H1, H0, H1n, H0n = (fitB, fitA, fitB_NB, fitA_NB) if boolEstimateNoiseBasedOnH0 else (fitA, fitB, fitA_NB, fitB_NB)
     objLP.lsFitConvergence = {
         "boolConvergenceH1": H1["boolConvergenceModel"], "boolConvergenceH0": H0["boolConvergenceModel"],

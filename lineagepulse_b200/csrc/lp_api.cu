@@ -48,6 +48,7 @@ struct lpb200_ctx {
     // stats
     lpb200_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaStream_t> aux_streams;   // for concurrent independent fits (lpb200_fit_model_multi)
     int use_table = 1;
     int no_fastpath = 0;   // LPB200_NO_FASTPATH=1: always run the generic evaluator (testing)
     int ctas_per_sm = LP_FAST_MINBLOCKS;  // persistent fit CTAs per SM (LPB200_CTAS_PER_SM overrides)
@@ -187,6 +188,22 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
         delete c;
         return nullptr;
     }
+    // load every fit-kernel variant now: with CUDA's lazy module loading the first launch of a kernel can
+    // wait for running kernels, which would serialise the concurrent fits of lpb200_fit_model_multi
+    {
+        const int smem = (int)sizeof(FitShared);
+        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_IMPULSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_IMPULSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_CONST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_CONST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_IMPULSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_IMPULSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_CONST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_CONST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaGetLastError();
+    }
     const char *e = getenv("LPB200_NO_TABLE");
     if (e && atoi(e)) c->use_table = 0;
     e = getenv("LPB200_CTAS_PER_SM");
@@ -216,6 +233,7 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (c->d_nnz) cudaFree(c->d_nnz);
     if (c->d_nobs) cudaFree(c->d_nobs);
     if (c->d_xchg) cudaFree(c->d_xchg);
+    for (cudaStream_t st : c->aux_streams) cudaStreamDestroy(st);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -598,7 +616,8 @@ static int fit_threads(int N) { return N >= 2048 ? 256 : 128; }
 struct DropBufs {
     DevBuf<double> drop, pi, l1m, pi_scr, l1m_scr;
 };
-static int setup_drop(lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p, int grid, FitArgs &A, DropBufs &B) {
+static int setup_drop(lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p, int grid, FitArgs &A, DropBufs &B,
+                      cudaStream_t stream) {
     const int N = ctx->N;
     A.drop = nullptr;
     A.pi_glob = A.l1m_glob = nullptr;
@@ -606,13 +625,13 @@ static int setup_drop(lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p
     if (M.drop_model == LPB200_DROP_NONE) return 0;
     if (!p->mat_drop) return set_err(ctx, LPB200_E_ARG, "mat_drop is NULL but the drop-out model is not \"none\"");
     CK(B.drop.alloc((size_t)N * M.q_drop));
-    CK(cudaMemcpyAsync(B.drop.p, p->mat_drop, sizeof(double) * (size_t)N * M.q_drop, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(B.drop.p, p->mat_drop, sizeof(double) * (size_t)N * M.q_drop, cudaMemcpyHostToDevice, stream));
     A.drop = B.drop.p;
     if (M.drop_model == LPB200_DROP_LOGISTIC) {
         if (ctx->D.P == 0) {
             CK(B.pi.alloc(N));
             CK(B.l1m.alloc(N));
-            pi_vector_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->D, M, B.drop.p, B.pi.p, B.l1m.p);
+            pi_vector_kernel<<<(N + 255) / 256, 256, 0, stream>>>(ctx->D, M, B.drop.p, B.pi.p, B.l1m.p);
             CK(cudaGetLastError());
             ctx->stats.launches++;
             A.pi_glob = B.pi.p;
@@ -648,7 +667,7 @@ static int eval_loglik_impl(lpb200_ctx *ctx, const DevModel &M, const lpb200_par
     A.ll_out = d_ll.p;
     A.use_table = ctx->use_table;
     DropBufs B;
-    int rc = setup_drop(ctx, M, p, grid, A, B);
+    int rc = setup_drop(ctx, M, p, grid, A, B, ctx->stream);
     if (rc) return rc;
     const size_t smem = sizeof(FitShared);
     if (ctx->is_u16) {
@@ -723,19 +742,45 @@ extern "C" int lpb200_impulse_starts(lpb200_ctx *ctx, double *peak, double *vall
 // ---------------------------------------------------------------------------------------------
 // fitMuDisp
 // ---------------------------------------------------------------------------------------------
-static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p, const lpb200_control *c, double *ll,
-                           int32_t *conv) {
+// One fitMuDisp call = one job: launch (asynchronous, on the job's stream) and collect (blocks on that
+// stream, selects the best start, writes the reference's outputs).  Independent jobs (the ZINB and NB
+// fits of fitLPModels) are launched on separate streams so that the persistent CTAs of the next kernel
+// fill the SMs the previous kernel's item-length tail leaves idle.
+struct FitJob {
+    DevModel M{};
+    lpb200_params *p = nullptr;
+    double *ll = nullptr;
+    int32_t *conv = nullptr;
+    int n = 0, n_starts = 1, grid = 0;
+    size_t n_items = 0;
+    std::vector<double> theta0;
+    DevBuf<double> d_theta0, d_theta_out, d_ll;
+    DevBuf<int> d_conv, d_queue;
+    DevBuf<unsigned> d_evals;
+    DropBufs B;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint64_t ole = 0, fn_evals = 0;
+    ~FitJob() {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+
+static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     const DevDesign &D = ctx->D;
+    const DevModel &M = J.M;
     const int G = ctx->G, N = ctx->N, n = M.n_theta, n_nat = lp_n_nat(M);
     const bool impulse = M.mu_model == LPB200_MU_IMPULSE;
-    const int n_starts = impulse ? 3 : 1;
+    J.n = n;
+    J.n_starts = impulse ? 3 : 1;
     int rc;
     if (impulse && (rc = ensure_starts(ctx))) return rc;
     std::vector<double> nat;
-    params_to_nat(ctx, M, p, nat);
+    params_to_nat(ctx, M, J.p, nat);
     // theta0 per (gene, start); impulse start order Peak, Valley, Prior (fitMeanDispersion.R:663)
-    const size_t n_items = (size_t)G * n_starts;
-    std::vector<double> theta0(n_items * n);
+    J.n_items = (size_t)G * J.n_starts;
+    J.theta0.resize(J.n_items * n);
     for (int i = 0; i < G; i++) {
         PointNat g;
         lp_nat_load(M, nat.data() + (size_t)i * n_nat, g);
@@ -747,44 +792,43 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
                 coords[2][k] = g.mu[k];
             }
             for (int k = 2; k < 5; k++) coords[2][k] = log(coords[2][k]);  // :621-622
-            for (int s = 0; s < 3; s++) lp_pack_theta(D, M, g, coords[s], theta0.data() + ((size_t)i * 3 + s) * n);
+            for (int s = 0; s < 3; s++) lp_pack_theta(D, M, g, coords[s], J.theta0.data() + ((size_t)i * 3 + s) * n);
         } else {
-            lp_pack_theta(D, M, g, nullptr, theta0.data() + (size_t)i * n);
+            lp_pack_theta(D, M, g, nullptr, J.theta0.data() + (size_t)i * n);
         }
     }
-    DevBuf<double> d_theta0, d_theta_out, d_ll;
-    DevBuf<int> d_conv, d_queue;
-    DevBuf<unsigned> d_evals;
-    CK(d_theta0.alloc(theta0.size()));
-    CK(d_theta_out.alloc(theta0.size()));
-    CK(d_ll.alloc(n_items));
-    CK(d_conv.alloc(n_items));
-    CK(d_evals.alloc(n_items));
-    CK(d_queue.alloc(1));
-    CK(cudaMemcpyAsync(d_theta0.p, theta0.data(), sizeof(double) * theta0.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(d_queue.p, 0, sizeof(int), ctx->stream));
+    CK(J.d_theta0.alloc(J.theta0.size()));
+    CK(J.d_theta_out.alloc(J.theta0.size()));
+    CK(J.d_ll.alloc(J.n_items));
+    CK(J.d_conv.alloc(J.n_items));
+    CK(J.d_evals.alloc(J.n_items));
+    CK(J.d_queue.alloc(1));
+    CK(cudaEventCreate(&J.e0));
+    CK(cudaEventCreate(&J.e1));
+    CK(cudaMemcpyAsync(J.d_theta0.p, J.theta0.data(), sizeof(double) * J.theta0.size(), cudaMemcpyHostToDevice, J.stream));
+    CK(cudaMemsetAsync(J.d_queue.p, 0, sizeof(int), J.stream));
     const int threads = fit_threads(N);
-    const int grid = (int)std::min<size_t>(n_items, (size_t)ctx->sm_count * ctx->ctas_per_sm);
+    const int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * ctx->ctas_per_sm);
+    J.grid = grid;
     FitArgs A{};
     A.D = D;
     A.M = M;
     A.C = count_view(ctx);
-    A.n_items = (int)n_items;
-    A.n_starts = n_starts;
-    A.queue = d_queue.p;
-    A.theta0 = d_theta0.p;
+    A.n_items = (int)J.n_items;
+    A.n_starts = J.n_starts;
+    A.queue = J.d_queue.p;
+    A.theta0 = J.d_theta0.p;
     A.maxit = c->maxit_mudisp;
     A.reltol = c->reltol_mudisp;
     A.ndeps = c->ndeps;
-    A.theta_out = d_theta_out.p;
-    A.ll_out = d_ll.p;
-    A.conv_out = d_conv.p;
-    A.evals_out = d_evals.p;
+    A.theta_out = J.d_theta_out.p;
+    A.ll_out = J.d_ll.p;
+    A.conv_out = J.d_conv.p;
+    A.evals_out = J.d_evals.p;
     A.use_table = ctx->use_table;
-    DropBufs B;
-    if ((rc = setup_drop(ctx, M, p, grid, A, B))) return rc;
+    if ((rc = setup_drop(ctx, M, J.p, grid, A, J.B, J.stream))) return rc;
     const size_t smem = sizeof(FitShared);
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaEventRecord(J.e0, J.stream));
     // specialised kernels for the hot configurations, generic kernel otherwise
     const bool fast = !ctx->no_fastpath && lp_disp_is_scalar(D, M) && D.n_conf_mu == 0 &&
                       (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE) &&
@@ -792,7 +836,7 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
 #define LP_LAUNCH_FIT(KERNEL)                                                                               \
     do {                                                                                                    \
         CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        KERNEL<<<grid, threads, smem, ctx->stream>>>(A);                                                   \
+        KERNEL<<<grid, threads, smem, J.stream>>>(A);                                                      \
     } while (0)
 #define LP_LAUNCH_FIT_CT(CT)                                                                                \
     do {                                                                                                    \
@@ -815,36 +859,34 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
 #undef LP_LAUNCH_FIT
     if (getenv("LPB200_DEBUG"))
         fprintf(stderr, "[lpb200] fit_mudisp: %s kernel (%s counts), mu=%d drop=%d items=%zu grid=%d threads=%d smem=%zu\n",
-                fast ? "specialised" : "generic", ctx->is_u16 ? "u16" : "i32", M.mu_model, M.drop_model, n_items, grid,
+                fast ? "specialised" : "generic", ctx->is_u16 ? "u16" : "i32", M.mu_model, M.drop_model, J.n_items, grid,
                 threads, smem);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventRecord(J.e1, J.stream));
     ctx->stats.launches++;
-    std::vector<double> theta_out(theta0.size()), ll_items(n_items);
+    return 0;
+}
+
+static int fit_collect(lpb200_ctx *ctx, FitJob &J, float *kernel_ms) {
+    const DevDesign &D = ctx->D;
+    const DevModel &M = J.M;
+    const int G = ctx->G, N = ctx->N, n = J.n, n_starts = J.n_starts;
+    const size_t n_items = J.n_items;
+    std::vector<double> theta_out(J.theta0.size()), ll_items(n_items);
     std::vector<int> conv_items(n_items);
     std::vector<unsigned> evals(n_items);
-    CK(cudaMemcpyAsync(theta_out.data(), d_theta_out.p, sizeof(double) * theta_out.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ll_items.data(), d_ll.p, sizeof(double) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(conv_items.data(), d_conv.p, sizeof(int) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(evals.data(), d_evals.p, sizeof(unsigned) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(theta_out.data(), J.d_theta_out.p, sizeof(double) * theta_out.size(), cudaMemcpyDeviceToHost, J.stream));
+    CK(cudaMemcpyAsync(ll_items.data(), J.d_ll.p, sizeof(double) * n_items, cudaMemcpyDeviceToHost, J.stream));
+    CK(cudaMemcpyAsync(conv_items.data(), J.d_conv.p, sizeof(int) * n_items, cudaMemcpyDeviceToHost, J.stream));
+    CK(cudaMemcpyAsync(evals.data(), J.d_evals.p, sizeof(unsigned) * n_items, cudaMemcpyDeviceToHost, J.stream));
+    CK(cudaStreamSynchronize(J.stream));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->stats.kernel_ms += ms;
-    if (getenv("LPB200_DEBUG") && n_starts > 1) {
-        double sum[3] = {0, 0, 0};
-        unsigned mx[3] = {0, 0, 0};
-        for (size_t it = 0; it < n_items; it++) {
-            sum[it % 3] += evals[it];
-            mx[it % 3] = std::max(mx[it % 3], evals[it]);
-        }
-        fprintf(stderr, "[lpb200] evals per start (peak, valley, prior): mean %.0f %.0f %.0f  max %u %u %u  kernel %.1f ms\n",
-                sum[0] / G, sum[1] / G, sum[2] / G, mx[0], mx[1], mx[2], ms);
-    }
+    cudaEventElapsedTime(&ms, J.e0, J.e1);
+    if (kernel_ms) *kernel_ms = ms;
     if (getenv("LPB200_DEBUG")) {
         // how well the dynamic queue balanced this launch: greedy list schedule of the measured item
         // costs (objective evaluations) on `grid` CTA slots, ideal / makespan
-        std::vector<double> slot(grid, 0.0);
+        std::vector<double> slot(J.grid, 0.0);
         double total = 0.0;
         unsigned longest = 0;
         for (size_t it = 0; it < n_items; it++) {
@@ -855,7 +897,7 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
         }
         double makespan = *std::max_element(slot.begin(), slot.end());
         fprintf(stderr, "[lpb200] fit_mudisp: %zu items, %.0f evaluations/item (max %u), kernel %.1f ms, queue balance %.3f\n",
-                n_items, total / n_items, longest, ms, total / grid / makespan);
+                n_items, total / n_items, longest, ms, total / J.grid / makespan);
     }
     bool nonfinite = false;
     for (int i = 0; i < G; i++) {
@@ -863,13 +905,13 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
         bool any_bad = false;
         for (int s = 0; s < n_starts; s++) {
             size_t it = (size_t)i * n_starts + s;
-            ctx->stats.fn_evals += evals[it];
-            ctx->stats.ole += (uint64_t)evals[it] * N;
+            J.fn_evals += evals[it];
+            J.ole += (uint64_t)evals[it] * N;
             if (conv_items[it] == 1001 || std::isnan(ll_items[it])) any_bad = true;
         }
         if (any_bad) {  // optim() error => the reference aborts (fitMeanDispersion.R:384-389)
-            ll[i] = NAN;
-            conv[i] = 1001;
+            J.ll[i] = NAN;
+            J.conv[i] = 1001;
             nonfinite = true;
             continue;
         }
@@ -880,12 +922,30 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
         lp_unpack_theta(D, M, theta_out.data() + it * n, g);  // same clamps as :391-498
         double v[LPB200_MAX_PARAMS * 3];
         lp_nat_store(M, g, v);
-        nat_to_params(ctx, M, v, i, p);
-        ll[i] = ll_items[it];
-        conv[i] = conv_items[it];
+        nat_to_params(ctx, M, v, i, J.p);
+        J.ll[i] = ll_items[it];
+        J.conv[i] = conv_items[it];
     }
+    ctx->stats.fn_evals += J.fn_evals;
+    ctx->stats.ole += J.ole;
     if (nonfinite) return set_err(ctx, LPB200_E_NONFINITE, "fitMuDisp: non-finite objective (optim would have raised an error)");
     return 0;
+}
+
+static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p, const lpb200_control *c, double *ll,
+                           int32_t *conv) {
+    FitJob J;
+    J.M = M;
+    J.p = p;
+    J.ll = ll;
+    J.conv = conv;
+    J.stream = ctx->stream;
+    int rc = fit_launch(ctx, J, c);
+    if (rc) return rc;
+    float ms = 0.f;
+    rc = fit_collect(ctx, J, &ms);
+    ctx->stats.kernel_ms += ms;
+    return rc;
 }
 
 extern "C" int lpb200_fit_mudisp(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll,
@@ -1223,6 +1283,83 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
     }
     *converged = (!any_nonconv && ll_new < ll_old * c->prec_em && ll_new > ll_old) ? 1 : 0;  // :342-347
     *n_iter = iter - 1;
+    return 0;
+}
+
+// Several independent fitModel() calls without drop-out estimation (the fits B, C, D of fitLPModels,
+// fitWrapperLP.R:152-238: each is initialisation + one fitMuDisp pass) run concurrently: their fit
+// kernels go to separate streams, so the persistent CTAs of one kernel take over the SMs that the
+// item-length tail of another leaves idle.  Results are identical to n_jobs sequential
+// lpb200_fit_model(fit_drop = 0) calls.
+extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_model *models, lpb200_params *params,
+                                      const lpb200_control *c, double min_rowmean_global, double *ll_init, double *em_ll,
+                                      int32_t *converged, double *ll, int32_t *conv, uint64_t *ole) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    enum { MAX_JOBS = 4 };
+    if (n_jobs < 1 || n_jobs > MAX_JOBS) return set_err(ctx, LPB200_E_ARG, "fit_model_multi: 1..%d jobs", (int)MAX_JOBS);
+    const int G = ctx->G;
+    FitJob jobs[MAX_JOBS];
+    for (int j = 0; j < n_jobs; j++) {
+        FitJob &J = jobs[j];
+        if ((rc = make_model(ctx, &models[j], J.M))) return rc;
+        J.p = &params[j];
+        J.ll = ll + (size_t)j * G;
+        J.conv = conv + (size_t)j * G;
+        if (J.M.drop_model != LPB200_DROP_NONE && !J.p->mat_drop)
+            return set_err(ctx, LPB200_E_ARG, "fit_model_multi: job %d needs the drop-out model as input", j);
+        if ((rc = init_params_impl(ctx, J.M, J.p, min_rowmean_global, false))) return rc;
+        if ((rc = eval_loglik_impl(ctx, J.M, J.p, J.ll))) return rc;  // fitModel.R:228-233
+        if ((rc = sum_ll(ctx, J.ll, G, &ll_init[j]))) return rc;
+    }
+    while ((int)ctx->aux_streams.size() < n_jobs - 1) {
+        cudaStream_t st;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(st);
+    }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));  // everything enqueued so far is visible to the auxiliary streams
+    for (int j = 0; j < n_jobs; j++) {
+        jobs[j].stream = (j == 0) ? ctx->stream : ctx->aux_streams[j - 1];
+        if (j > 0) CK(cudaStreamWaitEvent(jobs[j].stream, ctx->ev0, 0));
+        if ((rc = fit_launch(ctx, jobs[j], c))) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
+    }
+    int first_err = 0;
+    float span = 0.f;
+    for (int j = 0; j < n_jobs; j++) {
+        rc = fit_collect(ctx, jobs[j], nullptr);
+        if (rc && !first_err) first_err = rc;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, jobs[0].e0, jobs[j].e1);
+        span = std::max(span, ms);
+        if (getenv("LPB200_DEBUG")) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, jobs[0].e0, jobs[j].e0);
+            fprintf(stderr, "[lpb200] concurrent job %d: kernel from %.1f ms to %.1f ms\n", j, t0, ms);
+        }
+        if (ole) ole[j] = jobs[j].ole;
+    }
+    ctx->stats.kernel_ms += span;
+    if (first_err) return first_err;
+    for (int j = 0; j < n_jobs; j++) {
+        double ll_new;
+        if ((rc = sum_ll(ctx, jobs[j].ll, G, &ll_new))) return rc;
+        em_ll[j] = ll_new;
+        int any_nonconv = 0;
+        for (int i = 0; i < G; i++)
+            if (jobs[j].conv[i] != 0) any_nonconv = 1;
+        if (ctx->world > 1) {
+            double v = any_nonconv;
+            CK(cudaMemcpyAsync(ctx->d_xchg, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = do_allreduce(ctx, ctx->d_xchg, 1, LPB200_F64))) return rc;
+            CK(cudaMemcpyAsync(&v, ctx->d_xchg, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            any_nonconv = v > 0;
+        }
+        converged[j] = (!any_nonconv && ll_new < ll_init[j] * c->prec_em && ll_new > ll_init[j]) ? 1 : 0;
+    }
     return 0;
 }
 

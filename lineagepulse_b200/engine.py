@@ -168,6 +168,29 @@ class Engine:
         return dict(em_ll=em, n_iter=n_iter.value, converged=bool(converged.value), ll_init=ll_init.value,
                     ll=ll, conv=conv)
 
+    def fit_model_multi(self, jobs, control=None, min_rowmean_global=float("nan")):
+        """Independent fitModel() calls without drop-out estimation, run concurrently
+        (lpb200_fit_model_multi).  ``jobs`` = [(Model, ParamsData), ...]; returns one dict per job."""
+        control = control or A.default_control()
+        n, G = len(jobs), self.n_genes
+        models = (A.Model * n)(*[m for m, _ in jobs])
+        structs = (A.Params * n)(*[p.as_struct() for _, p in jobs])
+        ll_init, em = np.zeros(n), np.zeros(n)
+        converged = np.zeros(n, dtype=np.int32)
+        ll = np.zeros((n, G))
+        conv = np.zeros((n, G), dtype=np.int32)
+        ole = (C.c_uint64 * n)()
+        self._check(self.lib.lpb200_fit_model_multi(
+            self.ctx, n, models, structs, C.byref(control), min_rowmean_global, ll_init.ctypes.data_as(A.c_double_p),
+            em.ctypes.data_as(A.c_double_p), converged.ctypes.data_as(A.c_int32_p), ll.ctypes.data_as(A.c_double_p),
+            conv.ctypes.data_as(A.c_int32_p), ole))
+        out = []
+        for j, (_, p) in enumerate(jobs):
+            p.sync_back()
+            out.append(dict(em_ll=np.array([em[j]]), n_iter=1, converged=bool(converged[j]), ll_init=ll_init[j],
+                            ll=ll[j].copy(), conv=conv[j].copy(), ole=int(ole[j])))
+        return out
+
     def post_drop(self, model, params, gene_ids):
         ids = np.ascontiguousarray(gene_ids, dtype=np.int32)
         z = np.zeros((len(ids), self.n_cells), order="F")

@@ -15,6 +15,8 @@ d = A.DesignData(X.shape[0], X.shape[1], pseudotime=t, impulse_basis=ns(t, 4))
 e = Engine(0)
 e.load_counts_i32(X)
 e.set_design(d)
-t0 = time.time()
-res, work = bench.native_pipeline(e, d, A, float("nan"))
-print("pipeline s", time.time() - t0, {k: (v["ole"], round(v["kernel_ms"], 1)) for k, v in work.items()})
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+for _ in range(reps):
+    t0 = time.time()
+    res, work = bench.native_pipeline(e, d, A, float("nan"))
+    print("pipeline s", time.time() - t0, {k: (v["ole"], round(v["kernel_ms"], 1)) for k, v in work.items()})
