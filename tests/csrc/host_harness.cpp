@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../lineagepulse_b200/csrc/lp_bfgs.cuh"
 #include "../../lineagepulse_b200/csrc/lp_model.cuh"
+#include "../../lineagepulse_b200/csrc/lp_exact.cuh"
 
 static void make_dev(const lpb200_design *d, const lpb200_model *m, DevDesign &D, DevModel &M) {
     D.G = d->n_genes; D.N = d->n_cells; D.sf = d->size_factors; D.t = d->pseudotime; D.group = d->group_idx;
@@ -106,4 +107,12 @@ extern "C" double hh_ll_obs(double x, double mu, double phi, double pi) {
     double logphi = log(phi);
     if (x == 0) return pi >= 0 ? lp_ll_zero_zinb(mu, phi, pi) : lp_ll_zero_nb(mu, phi, logphi);
     return lp_ll_nonzero(x, lp_nb_xphi_part(x, phi), mu, phi, pi >= 0 ? log(1.0 - pi) : 0.0);
+}
+
+// exact fixed-point accumulation (lp_exact.cuh): result words for the given summation order
+extern "C" double hh_exact_sum(const double *v, int n, long long *words) {
+    ExactSum s = {0, 0, 0};
+    for (int i = 0; i < n; i++) lp_exact_add(s, v[i]);
+    words[0] = s.a; words[1] = s.b; words[2] = s.bad;
+    return lp_exact_value(s.a, s.b, s.bad);
 }

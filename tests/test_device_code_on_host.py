@@ -98,3 +98,24 @@ def test_device_objective_constant_model_fits_match_oracle(hh, oracle, c1):
         th, ll, cv, _ = _fit_gene(hh, d, m, X, i, th0, None, None, use_oracle_obs=False)
         assert abs(ll - rO["ll"][i]) <= 1e-8 * abs(rO["ll"][i])
         assert abs(np.exp(th[1]) - pO.mat_mu[i, 0]) <= 1e-5 * pO.mat_mu[i, 0]
+
+
+def test_exact_sum_is_order_independent(hh):
+    """lp_exact_add: the fixed-point words (and hence the value) do not depend on the summation order,
+    which is what makes an N-shard run bit-identical to the unsharded run."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    hh.hh_exact_sum.restype = C.c_double
+    v = np.ascontiguousarray(-rng.exponential(50.0, 5000) - rng.uniform(0, 1e-3, 5000))
+    w0 = (C.c_longlong * 3)()
+    r0 = hh.hh_exact_sum(v.ctypes.data_as(A.c_double_p), len(v), w0)
+    for _ in range(5):
+        p = np.ascontiguousarray(rng.permutation(v))
+        w = (C.c_longlong * 3)()
+        r = hh.hh_exact_sum(p.ctypes.data_as(A.c_double_p), len(p), w)
+        assert list(w) == list(w0) and r == r0
+    import math
+    assert abs(r0 - math.fsum(v)) <= 1e-15 * abs(math.fsum(v))     # and it is the correctly accumulated sum
+    bad = np.array([1.0, np.nan, 2.0])
+    wb = (C.c_longlong * 3)()
+    assert np.isnan(hh.hh_exact_sum(bad.ctypes.data_as(A.c_double_p), 3, wb)) and wb[2] == 1
