@@ -205,6 +205,50 @@ SEXP lp_fit_model(SEXP sctx, SEXP model, SEXP params, SEXP fit_drop, SEXP n_gene
     return out;
 }
 
+/* ---- fits B, C, D of fitLPModels (fitWrapperLP.R:152-238) in one concurrent call ------------------
+ * models: integer matrix 4 x n_jobs; params: list of n_jobs parameter lists (see params_of) */
+SEXP lp_fit_models(SEXP sctx, SEXP models, SEXP params, SEXP n_genes) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    int n_jobs = LENGTH(params), G = asInteger(n_genes);
+    lpb200_model *m = (lpb200_model *)R_alloc(n_jobs, sizeof(lpb200_model));
+    lpb200_params *p = (lpb200_params *)R_alloc(n_jobs, sizeof(lpb200_params));
+    for (int j = 0; j < n_jobs; j++) {
+        m[j].mu_model = INTEGER(models)[4 * j];
+        m[j].disp_model = INTEGER(models)[4 * j + 1];
+        m[j].drop_model = INTEGER(models)[4 * j + 2];
+        m[j].drop_fit_group = INTEGER(models)[4 * j + 3];
+        p[j] = params_of(VECTOR_ELT(params, j));
+    }
+    lpb200_control c;
+    lpb200_default_control(&c);
+    SEXP ll_init = PROTECT(allocVector(REALSXP, n_jobs)), em = PROTECT(allocVector(REALSXP, n_jobs));
+    SEXP convd = PROTECT(allocVector(INTSXP, n_jobs)), ll = PROTECT(allocVector(REALSXP, (long)n_jobs * G));
+    SEXP conv = PROTECT(allocVector(INTSXP, (long)n_jobs * G));
+    check(ctx, lpb200_fit_model_multi(ctx, n_jobs, m, p, &c, R_NaN, REAL(ll_init), REAL(em), INTEGER(convd), REAL(ll),
+                                      INTEGER(conv), NULL));
+    SEXP out = PROTECT(allocVector(VECSXP, 6));
+    SET_VECTOR_ELT(out, 0, params);
+    SET_VECTOR_ELT(out, 1, ll_init);
+    SET_VECTOR_ELT(out, 2, em);
+    SET_VECTOR_ELT(out, 3, convd);
+    SET_VECTOR_ELT(out, 4, ll);
+    SET_VECTOR_ELT(out, 5, conv);
+    UNPROTECT(6);
+    return out;
+}
+
+/* ---- getFitsMean / getFitsDispersion / getFitsDropout / getNormData / getPostDrop (getFits.R) -------- */
+SEXP lp_expand_fits(SEXP sctx, SEXP model, SEXP params, SEXP gene_ids, SEXP what, SEXP n_cells) {
+    lpb200_ctx *ctx = ctx_of(sctx);
+    lpb200_model m = model_of(model);
+    lpb200_params p = params_of(params);
+    int n = LENGTH(gene_ids);
+    SEXP z = PROTECT(allocVector(REALSXP, (long)n * asInteger(n_cells)));
+    check(ctx, lpb200_expand_fits(ctx, &m, &p, shift_idx(gene_ids), n, asInteger(what), REAL(z)));
+    UNPROTECT(1);
+    return z;
+}
+
 /* ---- LRT of runDEAnalysis (runHypothesisTests.R:81-86) -------------------------------------- */
 SEXP lp_lrt(SEXP ll_full, SEXP ll_red, SEXP ddf) {
     int G = LENGTH(ll_full);
@@ -226,6 +270,8 @@ static const R_CallMethodDef call_methods[] = {
     {"lp_fit_mudisp", (DL_FUNC)&lp_fit_mudisp, 4},
     {"lp_fit_pi", (DL_FUNC)&lp_fit_pi, 4},
     {"lp_fit_model", (DL_FUNC)&lp_fit_model, 5},
+    {"lp_fit_models", (DL_FUNC)&lp_fit_models, 4},
+    {"lp_expand_fits", (DL_FUNC)&lp_expand_fits, 6},
     {"lp_lrt", (DL_FUNC)&lp_lrt, 3},
     {NULL, NULL, 0}};
 
