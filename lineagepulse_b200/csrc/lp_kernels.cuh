@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256) impulse_starts_kernel(const __grid_consta
         // c = Q^T y,  y = log(x / s + 1)
         double c[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j = tid; j < N; j += blockDim.x) {
-            int x = lp_load_count(row, j);
+            int x = max(lp_load_count(row, j), 0);   // NA counts as 0 here, as in processSCData.R:262-264
             double s = D.sf ? D.sf[j] : 1.0;
             double y = log((double)x / s + 1.0);
 #pragma unroll
@@ -472,6 +472,8 @@ __global__ void __launch_bounds__(256) impulse_starts_kernel(const __grid_consta
             for (int which = 0; which < 2; which++) {
                 int i_tail = which == 0 ? mx_t.i : mn_t.i;
                 int i_head = which == 0 ? mx_h.i : mn_h.i;
+                if (i_tail < 0 || i_tail >= N) i_tail = min(1, N - 1);   // non-finite fits: never index out of range
+                if (i_head < 0 || i_head >= N) i_head = 0;
                 double T1 = (A.t_first + t[i_tail]) / 2.0;
                 double T2 = (t[i_head] + A.t_last) / 2.0;
                 if (T1 == A.t_first) {
@@ -1006,7 +1008,7 @@ __global__ void __launch_bounds__(256) spline_init_kernel(DevDesign D, CountView
         for (int k = 0; k < K; k++) {
             double s = 0.0;
             for (int j = threadIdx.x; j < D.N; j += blockDim.x)
-                s += Pinv[(size_t)k * D.N + j] * log((double)lp_load_count(row, j) + 1.0);
+                s += Pinv[(size_t)k * D.N + j] * log((double)max(lp_load_count(row, j), 0) + 1.0);   // NA as 0
             s = lp_block_sum(s, sh);
             if (threadIdx.x == 0) coef[gene + (size_t)k * D.G] = s;
         }

@@ -826,7 +826,7 @@ static void impulse_starts_gene(const int32_t *x, const lpb200_design *d, const 
     double *y = work, *fit = work + N;
     for (int j = 0; j < N; j++) {
         double sf = d->size_factors ? d->size_factors[j] : 1.0;
-        y[j] = log((double)x[j] / sf + 1);
+        y[j] = log((double)(x[j] < 0 ? 0 : x[j]) / sf + 1); /* NA counts as 0 (processSCData.R:262-264) */
     }
     thinqr_solve(qr, y, NULL, fit);
     for (int j = 0; j < N; j++) fit[j] = exp(fit[j]);
@@ -1233,7 +1233,10 @@ int lporacle_init_params(const int32_t *counts, const lpb200_design *d, const lp
         double *y = (double *)malloc(sizeof(double) * (size_t)N);
         double coef[16];
         for (int i = 0; i < G; i++) {
-            for (int j = 0; j < N; j++) y[j] = log((double)counts[(size_t)i * N + j] + 1);
+            for (int j = 0; j < N; j++) {
+                int32_t xv = counts[(size_t)i * N + j];
+                y[j] = log((double)(xv < 0 ? 0 : xv) + 1); /* NA counts as 0 */
+            }
             thinqr_solve(&qr, y, coef, NULL);
             for (int k = 0; k < pm; k++) out->mat_mu[i + (size_t)k * G] = coef[k];
         }
