@@ -77,15 +77,17 @@ LP_HD double lp_bd0(double x, double np) {
         if (fabs(s) < 2.2250738585072014e-308) return s;
         double ej = 2.0 * x * v;
         v = v * v;
-        ej *= v; s = s + ej * (1.0 / 3.0);
-        ej *= v; s = s + ej * (1.0 / 5.0);
-        ej *= v; s = s + ej * (1.0 / 7.0);
-        ej *= v; s = s + ej * (1.0 / 9.0);
-        ej *= v; s = s + ej * (1.0 / 11.0);
-        ej *= v; s = s + ej * (1.0 / 13.0);
-        ej *= v; s = s + ej * (1.0 / 15.0);
-        ej *= v; s = s + ej * (1.0 / 17.0);
-        ej *= v; s = s + ej * (1.0 / 19.0);
+        // explicit fma: the translation unit is compiled with -fmad=false (see the Makefile), these nine
+        // are the only fused operations of the likelihood code
+        ej *= v; s = fma(ej, 1.0 / 3.0, s);
+        ej *= v; s = fma(ej, 1.0 / 5.0, s);
+        ej *= v; s = fma(ej, 1.0 / 7.0, s);
+        ej *= v; s = fma(ej, 1.0 / 9.0, s);
+        ej *= v; s = fma(ej, 1.0 / 11.0, s);
+        ej *= v; s = fma(ej, 1.0 / 13.0, s);
+        ej *= v; s = fma(ej, 1.0 / 15.0, s);
+        ej *= v; s = fma(ej, 1.0 / 17.0, s);
+        ej *= v; s = fma(ej, 1.0 / 19.0, s);
         return s;
     }
     return x * log(x / np) + np - x;
