@@ -290,16 +290,19 @@ static void free_design(lpb200_ctx *c);
 static int finish_counts(lpb200_ctx *ctx, TmpCounts &tmp, int G, int N, size_t pitch) {
     int32_t *d_i32 = tmp.p;
     free_design(ctx);  // a design belongs to one matrix shape
+    // drop the previous matrix first: a failure below leaves the context in the "counts not loaded" state
+    if (ctx->d_counts) { cudaFree(ctx->d_counts); ctx->d_counts = nullptr; }
+    if (ctx->d_xmax) { cudaFree(ctx->d_xmax); ctx->d_xmax = nullptr; }
+    if (ctx->d_perm) { cudaFree(ctx->d_perm); ctx->d_perm = nullptr; }
+    if (ctx->d_nnz) { cudaFree(ctx->d_nnz); ctx->d_nnz = nullptr; }
+    if (ctx->d_nobs) { cudaFree(ctx->d_nobs); ctx->d_nobs = nullptr; }
+    ctx->G = ctx->N = 0;
     // row statistics, then narrow to uint16 when every count fits
     DevBuf<double> d_mean;
     CK(d_mean.alloc(G));
-    if (ctx->d_xmax) cudaFree(ctx->d_xmax);
     CK(cudaMalloc((void **)&ctx->d_xmax, sizeof(int32_t) * G));
     row_stats_kernel<<<G, 256, 0, ctx->stream>>>(d_i32, G, N, pitch, d_mean.p, ctx->d_xmax);
     CK(cudaGetLastError());
-    if (ctx->d_perm) cudaFree(ctx->d_perm);
-    if (ctx->d_nnz) cudaFree(ctx->d_nnz);
-    if (ctx->d_nobs) cudaFree(ctx->d_nobs);
     CK(cudaMalloc((void **)&ctx->d_perm, sizeof(uint32_t) * (size_t)G * pitch));
     CK(cudaMalloc((void **)&ctx->d_nnz, sizeof(int32_t) * G));
     CK(cudaMalloc((void **)&ctx->d_nobs, sizeof(int32_t) * G));
@@ -312,22 +315,25 @@ static int finish_counts(lpb200_ctx *ctx, TmpCounts &tmp, int G, int N, size_t p
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->global_max = 0;
     for (int v : xmax) ctx->global_max = std::max(ctx->global_max, v);
-    if (ctx->d_counts) { cudaFree(ctx->d_counts); ctx->d_counts = nullptr; }
-    ctx->G = G;
-    ctx->N = N;
-    ctx->pitch = pitch;
     if (ctx->global_max < (int)LP_NA_U16) {
         uint16_t *d16 = nullptr;
         CK(cudaMalloc((void **)&d16, sizeof(uint16_t) * (size_t)G * pitch));
         narrow_u16_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_i32, d16, (size_t)G * pitch);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(ctx->stream));
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(ctx->stream);
+        if (e1 != cudaSuccess) {
+            cudaFree(d16);
+            return set_err(ctx, LPB200_E_CUDA, "narrow_u16_kernel failed: %s", cudaGetErrorString(e1));
+        }
         ctx->d_counts = d16;   // tmp frees the int32 image
         ctx->is_u16 = true;
     } else {
         ctx->d_counts = tmp.release();
         ctx->is_u16 = false;
     }
+    ctx->G = G;
+    ctx->N = N;
+    ctx->pitch = pitch;
     ctx->stats.launches += 3;
     ctx->have_starts = false;
     return 0;
@@ -362,6 +368,11 @@ extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const dou
 extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32_t *p, const int32_t *i, const double *x) {
     if (!ctx) return LPB200_E_CUDA;
     if (G <= 0 || N <= 0 || !p) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: bad arguments");
+    if (p[0] != 0 || p[N] < 0 || (p[N] > 0 && (!i || !x))) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: bad column pointers");
+    for (int j = 0; j < N; j++)
+        if (p[j + 1] < p[j]) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: column pointers decrease at column %d", j);
+    for (int32_t e = 0; e < p[N]; e++)
+        if (i[e] < 0 || i[e] >= G) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: row index %d out of range", (int)i[e]);
     CK(cudaSetDevice(ctx->device));
     size_t nnz = (size_t)p[N];
     size_t pitch = row_pitch(N);
@@ -550,6 +561,23 @@ static int make_model(lpb200_ctx *ctx, const lpb200_model *m, DevModel &M) {
     return 0;
 }
 
+// the parameter matrices a model reads or writes must be there (R would stop with "subscript out of bounds")
+static int check_params(lpb200_ctx *ctx, const DevModel &M, const lpb200_params *p, bool need_drop) {
+    if (!p || !p->mat_mu || !p->mat_disp) return set_err(ctx, LPB200_E_ARG, "mat_mu / mat_disp is NULL");
+    if (ctx->D.n_conf_mu > 0 && !p->batch_mu) return set_err(ctx, LPB200_E_ARG, "batch_mu is NULL but the design has mean confounders");
+    if (ctx->D.n_conf_disp > 0 && !p->batch_disp)
+        return set_err(ctx, LPB200_E_ARG, "batch_disp is NULL but the design has dispersion confounders");
+    if (need_drop && M.drop_model != LPB200_DROP_NONE && !p->mat_drop)
+        return set_err(ctx, LPB200_E_ARG, "mat_drop is NULL but the drop-out model is not \"none\"");
+    return 0;
+}
+
+static const lpb200_control *control_or_default(const lpb200_control *c, lpb200_control &tmp) {
+    if (c) return c;
+    lpb200_default_control(&tmp);
+    return &tmp;
+}
+
 static int require_ready(lpb200_ctx *ctx) {
     if (!ctx) return LPB200_E_CUDA;
     if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "counts not loaded");
@@ -690,7 +718,9 @@ extern "C" int lpb200_eval_loglik(lpb200_ctx *ctx, const lpb200_model *m, const 
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
+    if (!m || !ll) return set_err(ctx, LPB200_E_ARG, "eval_loglik: NULL argument");
     if ((rc = make_model(ctx, m, M))) return rc;
+    if ((rc = check_params(ctx, M, p, true))) return rc;
     return eval_loglik_impl(ctx, M, p, ll);
 }
 
@@ -953,8 +983,11 @@ extern "C" int lpb200_fit_mudisp(lpb200_ctx *ctx, const lpb200_model *m, lpb200_
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
+    if (!m || !ll || !conv) return set_err(ctx, LPB200_E_ARG, "fit_mudisp: NULL argument");
     if ((rc = make_model(ctx, m, M))) return rc;
-    return fit_mudisp_impl(ctx, M, p, c, ll, conv);
+    if ((rc = check_params(ctx, M, p, true))) return rc;
+    lpb200_control tmp;
+    return fit_mudisp_impl(ctx, M, p, control_or_default(c, tmp), ll, conv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1137,8 +1170,11 @@ extern "C" int lpb200_fit_pi(lpb200_ctx *ctx, const lpb200_model *m, lpb200_para
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
+    if (!m || !ll || !conv) return set_err(ctx, LPB200_E_ARG, "fit_pi: NULL argument");
     if ((rc = make_model(ctx, m, M))) return rc;
-    return fit_pi_impl(ctx, M, m->drop_fit_group, p, c, ll, conv);
+    if ((rc = check_params(ctx, M, p, true))) return rc;
+    lpb200_control tmp;
+    return fit_pi_impl(ctx, M, m->drop_fit_group, p, control_or_default(c, tmp), ll, conv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1219,7 +1255,9 @@ extern "C" int lpb200_init_params(lpb200_ctx *ctx, const lpb200_model *m, lpb200
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
+    if (!m) return set_err(ctx, LPB200_E_ARG, "init_params: NULL argument");
     if ((rc = make_model(ctx, m, M))) return rc;
+    if ((rc = check_params(ctx, M, out, false))) return rc;
     return init_params_impl(ctx, M, out, min_rowmean_global, true);
 }
 
@@ -1249,7 +1287,11 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
+    if (!m || !em_ll || !n_iter || !converged || !ll || !conv) return set_err(ctx, LPB200_E_ARG, "fit_model: NULL argument");
     if ((rc = make_model(ctx, m, M))) return rc;
+    if ((rc = check_params(ctx, M, p, true))) return rc;
+    lpb200_control ctl_default;
+    c = control_or_default(c, ctl_default);
     const int G = ctx->G, N = ctx->N;
     if (fit_drop && M.drop_model == LPB200_DROP_NONE) fit_drop = 0;
     const int max_cycles = fit_drop ? c->max_cycles : 1;  // fitModel.R:181-183
@@ -1298,6 +1340,10 @@ extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_
     if (rc) return rc;
     enum { MAX_JOBS = 4 };
     if (n_jobs < 1 || n_jobs > MAX_JOBS) return set_err(ctx, LPB200_E_ARG, "fit_model_multi: 1..%d jobs", (int)MAX_JOBS);
+    if (!models || !params || !ll_init || !em_ll || !converged || !ll || !conv)
+        return set_err(ctx, LPB200_E_ARG, "fit_model_multi: NULL argument");
+    lpb200_control ctl_default;
+    c = control_or_default(c, ctl_default);
     const int G = ctx->G;
     FitJob jobs[MAX_JOBS];
     for (int j = 0; j < n_jobs; j++) {
@@ -1306,8 +1352,7 @@ extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_
         J.p = &params[j];
         J.ll = ll + (size_t)j * G;
         J.conv = conv + (size_t)j * G;
-        if (J.M.drop_model != LPB200_DROP_NONE && !J.p->mat_drop)
-            return set_err(ctx, LPB200_E_ARG, "fit_model_multi: job %d needs the drop-out model as input", j);
+        if ((rc = check_params(ctx, J.M, J.p, true))) return rc;
         if ((rc = init_params_impl(ctx, J.M, J.p, min_rowmean_global, false))) return rc;
         if ((rc = eval_loglik_impl(ctx, J.M, J.p, J.ll))) return rc;  // fitModel.R:228-233
         if ((rc = sum_ll(ctx, J.ll, G, &ll_init[j]))) return rc;
@@ -1377,7 +1422,9 @@ extern "C" int lpb200_expand_fits(lpb200_ctx *ctx, const lpb200_model *m, const 
     const bool needs_drop = kind == LPB200_EXPAND_DROP || kind == LPB200_EXPAND_POSTDROP;
     if (needs_drop && (M.drop_model == LPB200_DROP_NONE || !p->mat_drop))
         return set_err(ctx, LPB200_E_ARG, "this expansion needs a drop-out model");
+    if ((rc = check_params(ctx, M, p, false))) return rc;
     if (n_ids <= 0) return 0;
+    if (!gene_ids || !z) return set_err(ctx, LPB200_E_ARG, "expand_fits: NULL argument");
     const int G = ctx->G, N = ctx->N;
     for (int r = 0; r < n_ids; r++)
         if (gene_ids[r] < 0 || gene_ids[r] >= G) return set_err(ctx, LPB200_E_ARG, "gene id out of range");
