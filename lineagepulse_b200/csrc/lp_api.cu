@@ -1363,9 +1363,17 @@ extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_
         ctx->aux_streams.push_back(st);
     }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));  // everything enqueued so far is visible to the auxiliary streams
-    for (int j = 0; j < n_jobs; j++) {
-        jobs[j].stream = (j == 0) ? ctx->stream : ctx->aux_streams[j - 1];
-        if (j > 0) CK(cudaStreamWaitEvent(jobs[j].stream, ctx->ev0, 0));
+    // Launch the expensive fits first (impulse: 3 starts x 8 parameters) and the cheap ones last: a later
+    // kernel's CTAs become resident as the earlier kernel's persistent CTAs retire, so the cheap fit is
+    // what fills the item-length tail of the last expensive one.  The order does not change any result.
+    int order[MAX_JOBS];
+    for (int j = 0; j < n_jobs; j++) order[j] = j;
+    auto cost = [&](int j) { return (jobs[j].M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) * jobs[j].M.n_theta; };
+    std::stable_sort(order, order + n_jobs, [&](int a, int b) { return cost(a) > cost(b); });
+    for (int q = 0; q < n_jobs; q++) {
+        const int j = order[q];
+        jobs[j].stream = (q == 0) ? ctx->stream : ctx->aux_streams[q - 1];
+        if (q > 0) CK(cudaStreamWaitEvent(jobs[j].stream, ctx->ev0, 0));
         if ((rc = fit_launch(ctx, jobs[j], c))) {
             cudaDeviceSynchronize();
             return rc;
@@ -1377,11 +1385,11 @@ extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_
         rc = fit_collect(ctx, jobs[j], nullptr);
         if (rc && !first_err) first_err = rc;
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, jobs[0].e0, jobs[j].e1);
+        cudaEventElapsedTime(&ms, jobs[order[0]].e0, jobs[j].e1);
         span = std::max(span, ms);
         if (getenv("LPB200_DEBUG")) {
             float t0 = 0.f;
-            cudaEventElapsedTime(&t0, jobs[0].e0, jobs[j].e0);
+            cudaEventElapsedTime(&t0, jobs[order[0]].e0, jobs[j].e0);
             fprintf(stderr, "[lpb200] concurrent job %d: kernel from %.1f ms to %.1f ms\n", j, t0, ms);
         }
         if (ole) ole[j] = jobs[j].ole;
@@ -1544,5 +1552,23 @@ extern "C" int lpb200_fp64_peak(lpb200_ctx *ctx, double *tflops) {
     CK(cudaGetLastError());
     ctx->stats.launches += 4;
     *tflops = best;
+    return 0;
+}
+
+extern "C" int lpb200_libm_probe(lpb200_ctx *ctx, const double *x, int n, int use_library, double *exp_out, double *log_out) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (!x || !exp_out || !log_out || n <= 0) return set_err(ctx, LPB200_E_ARG, "libm_probe: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<double> dx, de, dl;
+    CK(dx.alloc(n));
+    CK(de.alloc(n));
+    CK(dl.alloc(n));
+    CK(cudaMemcpyAsync(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    libm_probe_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dx.p, n, use_library, de.p, dl.p);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    CK(cudaMemcpyAsync(exp_out, de.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(log_out, dl.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

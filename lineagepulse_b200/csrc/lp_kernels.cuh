@@ -128,7 +128,7 @@ __device__ void lp_eval_points(const FitArgs &A, FitShared &S, const CT *row, in
     const double *tabp = nullptr;
     if (scalar_phi) {
         phi_s = P.disp[0];
-        logphi_s = log(phi_s);
+        logphi_s = lp_log(phi_s);
         if (tab_len > 0) tabp = S.tab[S.tab_of_point[active ? k : 0]];
     }
     double acc = 0.0;
@@ -193,7 +193,7 @@ __device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *ro
     const bool active = k < nk;
     const PointNat &P = S.pts[active ? k : 0];
     const double phi = P.disp[0];
-    const double logphi = log(phi);
+    const double logphi = lp_log(phi);
     const double p0 = P.mu[0];
     double b2 = 0, h0 = 0, h1 = 0, h2 = 0, t1 = 0, t2 = 0, inv_h1 = 0;
     if (MU == LP_MU_FAST_IMPULSE) {
@@ -208,14 +208,19 @@ __device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *ro
     const uint32_t *perm = A.C.perm + (size_t)gene * A.C.pitch;
     const int nobs = A.C.nobs[gene], nnz = A.C.nnz[gene];
     if (active) {
-        for (int r = warp * cpw + slot; r < nobs; r += stride) {
-            const int j = (int)perm[r];
+        int r = warp * cpw + slot;
+        int j = (r < nobs) ? (int)perm[r] : 0;
+        for (; r < nobs; r += stride) {
+            // the next cell index is fetched one iteration ahead: the gathers below (count, pseudotime,
+            // drop-out rate) then hang off a register instead of a second dependent L2 access
+            const int r_next = r + stride;
+            const int j_next = (r_next < nobs) ? (int)perm[r_next] : 0;
             const int x = (r < nnz) ? lp_load_count(row, j) : 0;
             double mu;
             if (MU == LP_MU_FAST_IMPULSE) {
                 const double t = tt[j];
-                mu = inv_h1 * (h0 + (h1 - h0) * (1.0 / (1.0 + exp(-p0 * (t - t1))))) *
-                     (h2 + (h1 - h2) * (1.0 / (1.0 + exp(b2 * (t - t2)))));
+                mu = inv_h1 * (h0 + (h1 - h0) * (1.0 / (1.0 + lp_exp(-p0 * (t - t1))))) *
+                     (h2 + (h1 - h2) * (1.0 / (1.0 + lp_exp(b2 * (t - t2)))));
             } else {
                 mu = p0;
             }
@@ -229,6 +234,7 @@ __device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *ro
                 v = lp_ll_nonzero(xd, xphi, mus, phi, ZINB ? l1m_ptr[j] : 0.0);
             }
             acc += v;
+            j = j_next;
         }
     }
     for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -259,7 +265,7 @@ __device__ void lp_fixed_pi(const FitArgs &A, int gene, const double *&pi_ptr, c
     for (int j = threadIdx.x; j < D.N; j += blockDim.x) {
         double pi = lp_dropout_rate(lp_drop_lin(D, A.M, A.drop, gene, j, 1.0));
         ps[j] = pi;
-        ls[j] = log(1.0 - pi);
+        ls[j] = lp_log(1.0 - pi);
     }
     __syncthreads();
     pi_ptr = ps;
@@ -365,7 +371,7 @@ __global__ void pi_vector_kernel(DevDesign D, DevModel M, const double *drop, do
     if (j >= D.N) return;
     double p = lp_dropout_rate(lp_drop_lin(D, M, drop, 0, j, 1.0));
     pi[j] = p;
-    l1m[j] = log(1.0 - p);
+    l1m[j] = lp_log(1.0 - p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1024,4 +1030,17 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
         a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// exp / log of the inner loop (lp_libm.cuh) next to the CUDA math library's, for the bit-identity test
+__global__ void libm_probe_kernel(const double *x, int n, int use_library, double *e, double *l) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        if (use_library) {
+            e[k] = exp(x[k]);
+            l[k] = log(x[k]);
+        } else {
+            e[k] = lp_exp(x[k]);
+            l[k] = lp_log(x[k]);
+        }
+    }
 }

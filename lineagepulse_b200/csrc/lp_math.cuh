@@ -3,19 +3,20 @@
 // CPU-only test harness can run the same code.
 #pragma once
 #include "lp_common.cuh"
+#include "lp_libm.cuh"
 
 // evalImpulseModel (evalImpulseModel.R:23-37); p = (beta1, beta2, h0, h1, h2, t1, t2)
 LP_HD double lp_impulse(const double *p, double t) {
     double d1 = t - p[5];
     double d2 = t - p[6];
-    return (1.0 / p[3]) * (p[2] + (p[3] - p[2]) * (1.0 / (1.0 + exp(-p[0] * d1)))) *
-           (p[4] + (p[3] - p[4]) * (1.0 / (1.0 + exp(p[1] * d2))));
+    return (1.0 / p[3]) * (p[2] + (p[3] - p[2]) * (1.0 / (1.0 + lp_exp(-p[0] * d1)))) *
+           (p[4] + (p[3] - p[4]) * (1.0 / (1.0 + lp_exp(p[1] * d2))));
 }
 
 // evalDropoutModel (evalDropoutModel.R:24-32) given the linear predictor x'theta
 LP_HD double lp_dropout_rate(double lin) {
     const double off = 0.001;
-    return off + (1.0 - 2.0 * off) * 1.0 / (1.0 + exp(-lin));
+    return off + (1.0 - 2.0 * off) * 1.0 / (1.0 + lp_exp(-lin));
 }
 
 // ---- dnbinom(x, mu=, size=phi, log=TRUE) for x >= 1, restating R's nmath dnbinom_mu ->
@@ -37,8 +38,13 @@ LP_HD double lp_dropout_rate(double lin) {
      0.006665247032707682442356181, 0.006408994188004207068439631, 0.006171712263039457647534605, \
      0.005951370112758847735624416, 0.005746216513010115682026102, 0.00555473355196280137103869}
 static const double lp_sferr_host[31] = LP_SFERR_VALUES;
+// 1/3, 1/5, ..., 1/19 (correctly rounded quotients) for the bd0 series; in __constant__ memory on the
+// device for the same reason as the exp / log coefficients (lp_libm.cuh)
+#define LP_ODD_RECIP_VALUES {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0}
+static const double lp_odd_recip_host[9] = LP_ODD_RECIP_VALUES;
 #ifdef __CUDACC__
 __constant__ double lp_sferr_dev[31] = LP_SFERR_VALUES;
+__constant__ double lp_odd_recip_dev[9] = LP_ODD_RECIP_VALUES;
 #endif
 
 // stirlerr(n) = log(n!) - log(sqrt(2 pi n) (n/e)^n)
@@ -79,18 +85,24 @@ LP_HD double lp_bd0(double x, double np) {
         v = v * v;
         // explicit fma: the translation unit is compiled with -fmad=false (see the Makefile), these nine
         // are the only fused operations of the likelihood code
-        ej *= v; s = fma(ej, 1.0 / 3.0, s);
-        ej *= v; s = fma(ej, 1.0 / 5.0, s);
-        ej *= v; s = fma(ej, 1.0 / 7.0, s);
-        ej *= v; s = fma(ej, 1.0 / 9.0, s);
-        ej *= v; s = fma(ej, 1.0 / 11.0, s);
-        ej *= v; s = fma(ej, 1.0 / 13.0, s);
-        ej *= v; s = fma(ej, 1.0 / 15.0, s);
-        ej *= v; s = fma(ej, 1.0 / 17.0, s);
-        ej *= v; s = fma(ej, 1.0 / 19.0, s);
+#ifdef __CUDA_ARCH__
+#define LP_ODD_RECIP(k) lp_odd_recip_dev[k]
+#else
+#define LP_ODD_RECIP(k) lp_odd_recip_host[k]
+#endif
+        ej *= v; s = fma(ej, LP_ODD_RECIP(0), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(1), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(2), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(3), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(4), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(5), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(6), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(7), s);
+        ej *= v; s = fma(ej, LP_ODD_RECIP(8), s);
+#undef LP_ODD_RECIP
         return s;
     }
-    return x * log(x / np) + np - x;
+    return x * lp_log(x / np) + np - x;
 }
 
 // Part of dnbinom_mu that depends on (x, phi) only; tabulated per evaluation point when phi is
@@ -99,8 +111,8 @@ LP_HD double lp_bd0(double x, double np) {
 LP_HD double lp_nb_xphi_part(double x, double phi) {
     double n = x + phi;
     double xm = n - phi;
-    double lf = LP_LN_2PI + log(phi) + log1p(-phi / n);
-    return log(phi / (phi + x)) + (lp_stirlerr(n) - lp_stirlerr(phi) - lp_stirlerr(xm)) - 0.5 * lf;
+    double lf = LP_LN_2PI + lp_log(phi) + log1p(-phi / n);
+    return lp_log(phi / (phi + x)) + (lp_stirlerr(n) - lp_stirlerr(phi) - lp_stirlerr(xm)) - 0.5 * lf;
 }
 
 // Part that depends on mu: -bd0(phi, n p) - bd0(n - phi, n q)
@@ -121,7 +133,7 @@ LP_HD double lp_ll_nonzero(double x, double xphi, double mu, double phi, double 
 
 // Zero observation of the NB model: phi*(log(phi) - log(phi+mu)), floored (evalLogLik.R:40-42)
 LP_HD double lp_ll_zero_nb(double mu, double phi, double logphi) {
-    double v = phi * (logphi - log(phi + mu));
+    double v = phi * (logphi - lp_log(phi + mu));
     return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
 }
 
@@ -130,14 +142,14 @@ LP_HD double lp_ll_zero_nb(double mu, double phi, double logphi) {
 // of phi/(phi+mu) at huge phi is reproduced; the power is exp(phi*log(ratio)).
 LP_HD double lp_ll_zero_zinb(double mu, double phi, double pi) {
     double r = phi / (phi + mu);
-    double nb0 = exp(phi * log(r));
-    double v = log((1.0 - pi) * nb0 + pi);
+    double nb0 = lp_exp(phi * lp_log(r));
+    double v = lp_log((1.0 - pi) * nb0 + pi);
     return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
 }
 
 // posterior of drop-out at a zero (calcPostDrop.R:27-45)
 LP_HD double lp_post_drop_zero(double mu, double phi, double pi) {
-    double nb0 = exp(phi * log(phi / (phi + mu)));
+    double nb0 = lp_exp(phi * lp_log(phi / (phi + mu)));
     return pi / (pi + (1.0 - pi) * nb0);
 }
 

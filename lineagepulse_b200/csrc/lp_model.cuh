@@ -76,7 +76,7 @@ LP_HD double lp_mu_at(const DevDesign &D, const DevModel &M, const PointNat &g, 
     } else if (M.mu_model == LPB200_MU_SPLINES) {
         double lin = 0.0;
         for (int k = 0; k < D.k_mu; k++) lin += D.bs_mu[j + (size_t)k * D.N] * g.mu[k];
-        mu = exp(lin);
+        mu = lp_exp(lin);
     } else {
         mu = g.mu[D.group[j]];
     }
@@ -95,7 +95,7 @@ LP_HD double lp_disp_at(const DevDesign &D, const DevModel &M, const PointNat &g
     } else if (M.disp_model == LPB200_DISP_SPLINES) {
         double lin = 0.0;
         for (int k = 0; k < D.k_disp; k++) lin += D.bs_disp[j + (size_t)k * D.N] * g.disp[k];
-        phi = exp(lin);
+        phi = lp_exp(lin);
     } else {
         phi = g.disp[D.group[j]];
     }
@@ -114,7 +114,7 @@ LP_HD double lp_drop_lin(const DevDesign &D, const DevModel &M, const double *dr
     double lin = 1.0 * drop[j];
     k = 1;
     if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) {
-        lin += log(mu) * drop[j + (size_t)k * D.N];
+        lin += lp_log(mu) * drop[j + (size_t)k * D.N];
         k++;
     }
     for (int p = 0; p < D.P; p++, k++) lin += D.pi_pred[i + (size_t)p * D.G] * drop[j + (size_t)k * D.N];
@@ -141,12 +141,12 @@ LP_HD double lp_cell_ll(const DevDesign &D, const DevModel &M, const PointNat &g
         logphi = logphi_scalar;
     } else {
         phi = lp_disp_at(D, M, g, j);
-        logphi = log(phi);
+        logphi = lp_log(phi);
     }
     double pi = pi_fixed, l1m = l1m_fixed;
     if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) {
         pi = lp_dropout_rate(lp_drop_lin(D, M, drop, gene, j, mu));
-        l1m = log(1.0 - pi);
+        l1m = lp_log(1.0 - pi);
     }
     double mus = mu * s;
     if (x == 0) {

@@ -221,6 +221,14 @@ class Engine:
         self._check(self.lib.lpb200_fp64_peak(self.ctx, C.byref(v)))
         return v.value
 
+    def libm_probe(self, x, use_library: bool):
+        """exp(x), log(x) on the device: the inner loop's own implementation or the CUDA library's."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        e, l = np.zeros(len(x)), np.zeros(len(x))
+        self._check(self.lib.lpb200_libm_probe(self.ctx, x.ctypes.data_as(A.c_double_p), len(x), int(use_library),
+                                               e.ctypes.data_as(A.c_double_p), l.ctypes.data_as(A.c_double_p)))
+        return e, l
+
 
 def lrt(ll_full, ll_red, ddf, library_path=None):
     """LRT p-values and BH-adjusted p-values (runHypothesisTests.R:81-86).  Pure host arithmetic
