@@ -638,7 +638,7 @@ static CountView count_view(const lpb200_ctx *ctx) {
     return C;
 }
 
-static int fit_threads(int N) { return N >= 2048 ? 256 : 128; }
+static int fit_threads(int N) { return N >= 2048 ? LP_FIT_THREADS : 128; }
 
 // drop-out inputs shared by the fit / eval kernels
 struct DropBufs {

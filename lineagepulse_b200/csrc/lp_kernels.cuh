@@ -26,15 +26,21 @@
 #define LP_TAB 1024       // entries of one (x, phi) table
 #endif
 #define LP_NTAB 3         // tables per pass: base phi, phi + eps, phi - eps
-#define LP_MAX_WARPS 8
-#define LP_FIT_THREADS 256
+// Threads of a fit CTA (one CTA works on one (gene, start) item) and CTAs per SM: 32 warps per SM either
+// way (register cap 64).  512 x 2 instead of 256 x 4 halves the duration of an item and with it the
+// item-length tail of the dynamic queue (balance 0.86 -> 0.96 at 15 000 items, -4 % at 1 184 genes,
+// -0.4 % at 5 000); 1024 x 1 balances better still but loses 4 % to the longer barriers.
+#ifndef LP_FIT_THREADS
+#define LP_FIT_THREADS 512
+#endif
+#define LP_MAX_WARPS (LP_FIT_THREADS / 32)
 #define LP_PI_NP 8        // max drop-out parameters per cell (1 + ofMu + LPB200_MAX_PI_PRED)
 #define LP_PI_KP 16       // points per cell per round (2q)
 #ifndef LP_FAST_MINBLOCKS
-#define LP_FAST_MINBLOCKS 4     // CTAs per SM the specialised fit kernels are compiled for (register cap 64)
+#define LP_FAST_MINBLOCKS 2     // CTAs per SM the specialised fit kernels are compiled for (register cap 64)
 #endif
 #ifndef LP_GENERIC_MINBLOCKS
-#define LP_GENERIC_MINBLOCKS 4
+#define LP_GENERIC_MINBLOCKS 2
 #endif
 
 __device__ __forceinline__ int lp_load_count(const uint16_t *r, int j) {
