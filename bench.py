@@ -360,8 +360,8 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 # dram__bytes_read + write per launch from profiles/ncu_fit_mudisp_impulse_zinb_r1.csv
-                # (82.7 MB at 1 184 genes x 10 000 cells, u16 counts), scaled to this launch's matrix
-                "traffic": 82.65e6 * (G * N) / (1184.0 * 10000.0) * ((ct_bytes + 4.0) / 6.0),
+                # (110.4 MB read + 44.4 MB written at 1 184 genes x 10 000 cells, u16 counts), scaled to this launch's matrix
+                "traffic": 154.74e6 * (G * N) / (1184.0 * 10000.0) * ((ct_bytes + 4.0) / 6.0),
                 "traffic_unit": "bytes per launch (ncu, scaled by matrix size)",
                 "kernel": f"fit_mudisp_kernel<{ct_name}> (fits B, C, D: three overlapping launches)",
                 "kernel_share_of_step": share,
