@@ -225,8 +225,9 @@ __device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *ro
             double mu;
             if (MU == LP_MU_FAST_IMPULSE) {
                 const double t = tt[j];
-                mu = inv_h1 * (h0 + (h1 - h0) * (1.0 / (1.0 + lp_exp(-p0 * (t - t1))))) *
-                     (h2 + (h1 - h2) * (1.0 / (1.0 + lp_exp(b2 * (t - t2)))));
+                double e1, e2;
+                lp_exp_pair(-p0 * (t - t1), b2 * (t - t2), e1, e2);
+                mu = inv_h1 * (h0 + (h1 - h0) * (1.0 / (1.0 + e1))) * (h2 + (h1 - h2) * (1.0 / (1.0 + e2)));
             } else {
                 mu = p0;
             }
@@ -1045,7 +1046,11 @@ __global__ void libm_probe_kernel(const double *x, int n, int use_library, doubl
             e[k] = exp(x[k]);
             l[k] = log(x[k]);
         } else {
-            e[k] = lp_exp(x[k]);
+            // even entries through the single routine, odd entries through the pair routine (partner: the
+            // previous argument), so both are compared with the library
+            double partner;
+            if (k & 1) lp_exp_pair(x[k - 1], x[k], partner, e[k]);
+            else e[k] = lp_exp(x[k]);
             l[k] = lp_log(x[k]);
         }
     }
