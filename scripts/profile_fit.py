@@ -1,5 +1,5 @@
 """Profiling driver: one pass of fits A-D + LRT on a matrix sized for one full wave of CTAs
-(592 genes x 10 000 cells: 148 SMs x 4 CTAs), used under ncu (see profiles/README.md)."""
+(default 592 genes x 10 000 cells), used under ncu (see profiles/README.md)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
