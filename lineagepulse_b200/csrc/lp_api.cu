@@ -838,7 +838,10 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     CK(cudaMemcpyAsync(J.d_theta0.p, J.theta0.data(), sizeof(double) * J.theta0.size(), cudaMemcpyHostToDevice, J.stream));
     CK(cudaMemsetAsync(J.d_queue.p, 0, sizeof(int), J.stream));
     const int threads = fit_threads(N);
-    const int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * ctx->ctas_per_sm);
+    // persistent CTAs: as many as stay resident (64 registers per thread; shared memory allows 4 per SM)
+    const int smem_limit = (int)((227 * 1024) / (sizeof(FitShared) + 1024));
+    const int per_sm = std::max(1, std::min(ctx->ctas_per_sm * (LP_FIT_THREADS / threads), smem_limit));
+    const int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * per_sm);
     J.grid = grid;
     FitArgs A{};
     A.D = D;
