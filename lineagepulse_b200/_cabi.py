@@ -299,6 +299,7 @@ def declare_product_prototypes(lib):
         "lpb200_reset_stats": (C.c_int, [vp]),
         "lpb200_fp64_peak": (C.c_int, [vp, c_double_p]),
         "lpb200_libm_probe": (C.c_int, [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
+        "lpb200_div_probe": (C.c_int, [vp, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError => the library does not export the ABI

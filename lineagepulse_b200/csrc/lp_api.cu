@@ -1575,3 +1575,24 @@ extern "C" int lpb200_libm_probe(lpb200_ctx *ctx, const double *x, int n, int us
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+extern "C" int lpb200_div_probe(lpb200_ctx *ctx, const double *a, const double *b, int n, int use_library, double *quot_out,
+                                double *rcp_out) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (!a || !b || !quot_out || !rcp_out || n <= 0) return set_err(ctx, LPB200_E_ARG, "div_probe: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<double> da, db, dq, dr;
+    CK(da.alloc(n));
+    CK(db.alloc(n));
+    CK(dq.alloc(n));
+    CK(dr.alloc(n));
+    CK(cudaMemcpyAsync(da.p, a, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    div_probe_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(da.p, db.p, n, use_library, dq.p, dr.p);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    CK(cudaMemcpyAsync(quot_out, dq.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(rcp_out, dr.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

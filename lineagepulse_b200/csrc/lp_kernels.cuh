@@ -225,9 +225,9 @@ __device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *ro
             double mu;
             if (MU == LP_MU_FAST_IMPULSE) {
                 const double t = tt[j];
-                double e1, e2;
-                lp_exp_pair(-p0 * (t - t1), b2 * (t - t2), e1, e2);
-                mu = inv_h1 * (h0 + (h1 - h0) * (1.0 / (1.0 + e1))) * (h2 + (h1 - h2) * (1.0 / (1.0 + e2)));
+                double s1, s2;
+                lp_sigmoid_pair(-p0 * (t - t1), b2 * (t - t2), s1, s2);
+                mu = inv_h1 * (h0 + (h1 - h0) * s1) * (h2 + (h1 - h2) * s2);
             } else {
                 mu = p0;
             }
@@ -1052,6 +1052,19 @@ __global__ void libm_probe_kernel(const double *x, int n, int use_library, doubl
             if (k & 1) lp_exp_pair(x[k - 1], x[k], partner, e[k]);
             else e[k] = lp_exp(x[k]);
             l[k] = lp_log(x[k]);
+        }
+    }
+}
+
+// a / b and 1 / b by the check-free fast paths of lp_libm.cuh next to the compiler's division
+__global__ void div_probe_kernel(const double *a, const double *b, int n, int use_library, double *q, double *r) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        if (use_library) {
+            q[k] = a[k] / b[k];
+            r[k] = 1.0 / b[k];
+        } else {
+            q[k] = lp_div<true>(a[k], b[k]);
+            r[k] = lp_rcp<true>(b[k]);
         }
     }
 }

@@ -6,11 +6,26 @@
 #include "lp_libm.cuh"
 
 // evalImpulseModel (evalImpulseModel.R:23-37); p = (beta1, beta2, h0, h1, h2, t1, t2)
+// The two sigmoids 1 / (1 + e): with both exponentials below 1e300 (not infinite, not NaN) the reciprocals
+// take the check-free path of lp_libm.cuh.
+LP_HD void lp_sigmoid_pair(double a1, double a2, double &s1, double &s2) {
+    double e1, e2;
+    lp_exp_pair(a1, a2, e1, e2);
+    if (e1 < 1e300 && e2 < 1e300) {
+        s1 = lp_rcp<true>(1.0 + e1);
+        s2 = lp_rcp<true>(1.0 + e2);
+    } else {
+        s1 = lp_rcp<false>(1.0 + e1);
+        s2 = lp_rcp<false>(1.0 + e2);
+    }
+}
+
 LP_HD double lp_impulse(const double *p, double t) {
     double d1 = t - p[5];
     double d2 = t - p[6];
-    return (1.0 / p[3]) * (p[2] + (p[3] - p[2]) * (1.0 / (1.0 + lp_exp(-p[0] * d1)))) *
-           (p[4] + (p[3] - p[4]) * (1.0 / (1.0 + lp_exp(p[1] * d2))));
+    double s1, s2;
+    lp_sigmoid_pair(-p[0] * d1, p[1] * d2, s1, s2);
+    return (1.0 / p[3]) * (p[2] + (p[3] - p[2]) * s1) * (p[4] + (p[3] - p[4]) * s2);
 }
 
 // evalDropoutModel (evalDropoutModel.R:24-32) given the linear predictor x'theta
@@ -76,9 +91,10 @@ LP_HD double lp_stirlerr(double n) {
 // (2j+1) become multiplications by the rounded reciprocals (<= 1 ulp of a term that is itself a
 // small correction).  The early-exit / division form cost 29 % of the fit kernel's instructions
 // (profiles/README.md) and diverged between lanes.
-LP_HD double lp_bd0(double x, double np) {
+template <bool FAST>
+LP_HD double lp_bd0_t(double x, double np) {
     if (fabs(x - np) < 0.1 * (x + np)) {
-        double v = (x - np) / (x + np);
+        double v = lp_div<FAST>(x - np, x + np);
         double s = (x - np) * v;
         if (fabs(s) < 2.2250738585072014e-308) return s;
         double ej = 2.0 * x * v;
@@ -102,8 +118,13 @@ LP_HD double lp_bd0(double x, double np) {
 #undef LP_ODD_RECIP
         return s;
     }
-    return x * lp_log(x / np) + np - x;
+    return x * lp_log(lp_div<FAST>(x, np)) + np - x;
 }
+LP_HD double lp_bd0(double x, double np) { return lp_bd0_t<false>(x, np); }
+
+// mu and phi both in (1e-150, 1e150): every quotient of the NB / ZINB terms (p, q, x / np, (x - np) / (x + np)
+// with 1 <= x < 2^31) then lies within [1e-290, 1e290] and may use the check-free division
+LP_HD bool lp_div_safe(double mu, double phi) { return mu > 1e-150 && mu < 1e150 && phi > 1e-150 && phi < 1e150; }
 
 // Part of dnbinom_mu that depends on (x, phi) only; tabulated per evaluation point when phi is
 // one scalar per gene.  n = x + phi and xm = n - phi are formed as R forms them (so the loss of
@@ -116,11 +137,15 @@ LP_HD double lp_nb_xphi_part(double x, double phi) {
 }
 
 // Part that depends on mu: -bd0(phi, n p) - bd0(n - phi, n q)
-LP_HD double lp_nb_mu_part(double x, double mu, double phi) {
+template <bool FAST>
+LP_HD double lp_nb_mu_part_t(double x, double mu, double phi) {
     double n = x + phi;
-    double p = phi / (phi + mu), q = mu / (phi + mu);
+    double p = lp_div<FAST>(phi, phi + mu), q = lp_div<FAST>(mu, phi + mu);
     if (p == 0.0 || q == 0.0) return -INFINITY;  // dbinom_raw: R_D__0
-    return -lp_bd0(phi, n * p) - lp_bd0(n - phi, n * q);
+    return -lp_bd0_t<FAST>(phi, n * p) - lp_bd0_t<FAST>(n - phi, n * q);
+}
+LP_HD double lp_nb_mu_part(double x, double mu, double phi) {
+    return lp_div_safe(mu, phi) ? lp_nb_mu_part_t<true>(x, mu, phi) : lp_nb_mu_part_t<false>(x, mu, phi);
 }
 
 // Non-zero observation: dnbinom(x, mu, size=phi, log) [+ log(1-pi)], floored
@@ -141,7 +166,7 @@ LP_HD double lp_ll_zero_nb(double mu, double phi, double logphi) {
 // (evalLogLik.R:125-132).  The ratio is formed exactly as the reference forms it, so the rounding
 // of phi/(phi+mu) at huge phi is reproduced; the power is exp(phi*log(ratio)).
 LP_HD double lp_ll_zero_zinb(double mu, double phi, double pi) {
-    double r = phi / (phi + mu);
+    double r = lp_div_safe(mu, phi) ? lp_div<true>(phi, phi + mu) : lp_div<false>(phi, phi + mu);
     double nb0 = lp_exp(phi * lp_log(r));
     double v = lp_log((1.0 - pi) * nb0 + pi);
     return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;

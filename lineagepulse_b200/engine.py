@@ -229,6 +229,16 @@ class Engine:
                                                e.ctypes.data_as(A.c_double_p), l.ctypes.data_as(A.c_double_p)))
         return e, l
 
+    def div_probe(self, a, b, use_library: bool):
+        """a / b and 1 / b on the device: the inner loop's check-free division or the compiler's."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        q, r = np.zeros(len(a)), np.zeros(len(a))
+        self._check(self.lib.lpb200_div_probe(self.ctx, a.ctypes.data_as(A.c_double_p), b.ctypes.data_as(A.c_double_p),
+                                              len(a), int(use_library), q.ctypes.data_as(A.c_double_p),
+                                              r.ctypes.data_as(A.c_double_p)))
+        return q, r
+
 
 def lrt(ll_full, ll_red, ddf, library_path=None):
     """LRT p-values and BH-adjusted p-values (runHypothesisTests.R:81-86).  Pure host arithmetic
