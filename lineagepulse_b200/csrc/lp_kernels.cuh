@@ -1051,7 +1051,9 @@ __global__ void libm_probe_kernel(const double *x, int n, int use_library, doubl
             double partner;
             if (k & 1) lp_exp_pair(x[k - 1], x[k], partner, e[k]);
             else e[k] = lp_exp(x[k]);
-            l[k] = lp_log(x[k]);
+            // positive normal finite arguments also go through the routine without the special-case tests
+            const bool plain = x[k] >= 2.2250738585072014e-308 && x[k] <= 1.7976931348623157e308;
+            l[k] = (plain && (k & 2)) ? lp_logp<true>(x[k]) : lp_log(x[k]);
         }
     }
 }

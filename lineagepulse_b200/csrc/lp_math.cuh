@@ -118,7 +118,7 @@ LP_HD double lp_bd0_t(double x, double np) {
 #undef LP_ODD_RECIP
         return s;
     }
-    return x * lp_log(lp_div<FAST>(x, np)) + np - x;
+    return x * lp_logp<FAST>(lp_div<FAST>(x, np)) + np - x;
 }
 LP_HD double lp_bd0(double x, double np) { return lp_bd0_t<false>(x, np); }
 
@@ -141,7 +141,7 @@ template <bool FAST>
 LP_HD double lp_nb_mu_part_t(double x, double mu, double phi) {
     double n = x + phi;
     double p = lp_div<FAST>(phi, phi + mu), q = lp_div<FAST>(mu, phi + mu);
-    if (p == 0.0 || q == 0.0) return -INFINITY;  // dbinom_raw: R_D__0
+    if (!FAST && (p == 0.0 || q == 0.0)) return -INFINITY;  // dbinom_raw: R_D__0 (FAST: p, q >= 1e-300)
     return -lp_bd0_t<FAST>(phi, n * p) - lp_bd0_t<FAST>(n - phi, n * q);
 }
 LP_HD double lp_nb_mu_part(double x, double mu, double phi) {
@@ -165,11 +165,15 @@ LP_HD double lp_ll_zero_nb(double mu, double phi, double logphi) {
 // Zero observation of the ZINB model: log((1-pi)*(phi/(phi+mu))^phi + pi), floored
 // (evalLogLik.R:125-132).  The ratio is formed exactly as the reference forms it, so the rounding
 // of phi/(phi+mu) at huge phi is reproduced; the power is exp(phi*log(ratio)).
-LP_HD double lp_ll_zero_zinb(double mu, double phi, double pi) {
-    double r = lp_div_safe(mu, phi) ? lp_div<true>(phi, phi + mu) : lp_div<false>(phi, phi + mu);
-    double nb0 = lp_exp(phi * lp_log(r));
+template <bool FAST>
+LP_HD double lp_ll_zero_zinb_t(double mu, double phi, double pi) {
+    double r = lp_div<FAST>(phi, phi + mu);
+    double nb0 = lp_exp(phi * lp_logp<FAST>(r));
     double v = lp_log((1.0 - pi) * nb0 + pi);
     return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
+}
+LP_HD double lp_ll_zero_zinb(double mu, double phi, double pi) {
+    return lp_div_safe(mu, phi) ? lp_ll_zero_zinb_t<true>(mu, phi, pi) : lp_ll_zero_zinb_t<false>(mu, phi, pi);
 }
 
 // posterior of drop-out at a zero (calcPostDrop.R:27-45)
