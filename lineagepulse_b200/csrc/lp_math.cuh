@@ -122,9 +122,10 @@ LP_HD double lp_bd0_t(double x, double np) {
 }
 LP_HD double lp_bd0(double x, double np) { return lp_bd0_t<false>(x, np); }
 
-// mu and phi both in (1e-150, 1e150): every quotient of the NB / ZINB terms (p, q, x / np, (x - np) / (x + np)
-// with 1 <= x < 2^31) then lies within [1e-290, 1e290] and may use the check-free division
-LP_HD bool lp_div_safe(double mu, double phi) { return mu > 1e-150 && mu < 1e150 && phi > 1e-150 && phi < 1e150; }
+// mu and phi both in (1e-100, 1e100): p, q >= 5e-201, n p and n q >= 5e-201, and every quotient of the NB / ZINB
+// terms (p, q, x / np <= 2^31 / 5e-201, (phi + mu) / n >= 1e-200, (x - np) / (x + np) with 1 <= x < 2^31) lies
+// well within [1e-290, 1e290]: the check-free division and logarithm apply
+LP_HD bool lp_div_safe(double mu, double phi) { return mu > 1e-100 && mu < 1e100 && phi > 1e-100 && phi < 1e100; }
 
 // Part of dnbinom_mu that depends on (x, phi) only; tabulated per evaluation point when phi is
 // one scalar per gene.  n = x + phi and xm = n - phi are formed as R forms them (so the loss of
