@@ -11,7 +11,7 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 LIB = os.path.join(BUILD, "libhostharness.so")
 SRC = os.path.join(ROOT, "tests", "csrc", "host_harness.cpp")
 HDRS = [os.path.join(ROOT, "lineagepulse_b200", "csrc", h) for h in
-        ("lp_common.cuh", "lp_math.cuh", "lp_model.cuh", "lp_bfgs.cuh", "lp_exact.cuh")]
+        ("lp_common.cuh", "lp_math.cuh", "lp_libm.cuh", "lp_model.cuh", "lp_bfgs.cuh", "lp_exact.cuh")]
 
 
 def build():
