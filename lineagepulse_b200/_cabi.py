@@ -286,6 +286,8 @@ def declare_product_prototypes(lib):
         "lpb200_eval_loglik": (C.c_int, [vp, P(Model), P(Params), c_double_p]),
         "lpb200_impulse_starts": (C.c_int, [vp, c_double_p, c_double_p]),
         "lpb200_fit_mudisp": (C.c_int, [vp, P(Model), P(Params), P(Control), c_double_p, c_int32_p]),
+        "lpb200_fit_mudisp_items": (C.c_int, [vp, P(Model), P(Params), P(Control), c_double_p, c_int32_p, c_int32_p, c_int32_p,
+                                              c_double_p, c_double_p, c_double_p, c_int32_p, P(C.c_uint32)]),
         "lpb200_fit_pi": (C.c_int, [vp, P(Model), P(Params), P(Control), c_double_p, c_int32_p]),
         "lpb200_fit_model": (C.c_int, [vp, P(Model), P(Params), C.c_int, P(Control), C.c_double,
                                        c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_int32_p]),
@@ -300,6 +302,7 @@ def declare_product_prototypes(lib):
         "lpb200_fp64_peak": (C.c_int, [vp, c_double_p]),
         "lpb200_libm_probe": (C.c_int, [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
         "lpb200_div_probe": (C.c_int, [vp, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p]),
+        "lpb200_rcp64h_probe": (C.c_int, [vp, c_int32_p, C.c_int, C.c_int32, c_int32_p, c_int32_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError => the library does not export the ABI

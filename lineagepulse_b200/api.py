@@ -198,16 +198,19 @@ def _prepare(matCounts, lsMuModel, lsDispModel, lsDropModel):
 
 
 def _params_from_models(design, model, lsMuModel, lsDispModel, lsDropModel) -> A.ParamsData:
+    """Copies: the library updates parameter matrices in place, R functions have value semantics -- the caller's
+    lsMuModel / lsDispModel / lsDropModel stay as they were."""
+    def own(a, rows):
+        return np.array(np.asarray(a, dtype=np.float64).reshape(rows, -1), dtype=np.float64, order="F", copy=True)
     p = A.ParamsData(design, model)
-    p.mat_mu = np.asfortranarray(np.asarray(lsMuModel["matMuModel"], dtype=np.float64).reshape(design.n_genes, -1))
-    p.mat_disp = np.asfortranarray(np.asarray(lsDispModel["matDispModel"], dtype=np.float64).reshape(design.n_genes, -1))
+    p.mat_mu = own(lsMuModel["matMuModel"], design.n_genes)
+    p.mat_disp = own(lsDispModel["matDispModel"], design.n_genes)
     if design.n_batches_mu:
-        p.batch_mu = [np.asfortranarray(b, dtype=np.float64) for b in lsMuModel["lsmatBatchModel"]]
+        p.batch_mu = [own(b, design.n_genes) for b in lsMuModel["lsmatBatchModel"]]
     if design.n_batches_disp:
-        p.batch_disp = [np.asfortranarray(b, dtype=np.float64) for b in lsDispModel["lsmatBatchModel"]]
+        p.batch_disp = [own(b, design.n_genes) for b in lsDispModel["lsmatBatchModel"]]
     if model.drop_model != A.DROP_NONE:
-        p.mat_drop = np.asfortranarray(np.asarray(lsDropModel["matDropoutLinModel"], dtype=np.float64)
-                                       .reshape(design.n_cells, -1))
+        p.mat_drop = own(lsDropModel["matDropoutLinModel"], design.n_cells)
     return p
 
 

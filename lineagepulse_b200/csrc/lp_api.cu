@@ -52,7 +52,27 @@ struct lpb200_ctx {
     int use_table = 1;
     int no_fastpath = 0;   // LPB200_NO_FASTPATH=1: always run the generic evaluator (testing)
     int ctas_per_sm = LP_FAST_MINBLOCKS;  // persistent fit CTAs per SM (LPB200_CTAS_PER_SM overrides)
+    int cluster = 0;       // CTAs per work item of the fit kernel; 0: chosen per launch (LPB200_CLUSTER = 1 | 2 | 4 overrides)
 };
+
+// The fit-kernel variants: count type (uint16_t / int32_t) x evaluator (generic; constant or impulse mean x NB or ZINB)
+// x launched as thread-block clusters or not.
+typedef void (*FitKernelFn)(const FitArgs);
+template <typename CT, bool CL>
+static FitKernelFn fit_kernel_ct(int variant) {
+    switch (variant) {
+    case 1: return fit_mudisp_kernel<CT, LP_MU_FAST_CONST, false, CL>;
+    case 2: return fit_mudisp_kernel<CT, LP_MU_FAST_CONST, true, CL>;
+    case 3: return fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, false, CL>;
+    case 4: return fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, true, CL>;
+    default: return fit_mudisp_kernel<CT, -1, false, CL>;
+    }
+}
+static FitKernelFn fit_kernel(bool u16, int variant, bool cl) {
+    if (u16) return cl ? fit_kernel_ct<uint16_t, true>(variant) : fit_kernel_ct<uint16_t, false>(variant);
+    return cl ? fit_kernel_ct<int32_t, true>(variant) : fit_kernel_ct<int32_t, false>(variant);
+}
+static size_t fit_smem_bytes(bool cl) { return cl ? sizeof(FitSharedT<true>) : sizeof(FitSharedT<false>); }
 
 static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -190,26 +210,23 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
     }
     // load every fit-kernel variant now: with CUDA's lazy module loading the first launch of a kernel can
     // wait for running kernels, which would serialise the concurrent fits of lpb200_fit_model_multi
-    {
-        const int smem = (int)sizeof(FitShared);
-        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_IMPULSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_IMPULSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_CONST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, LP_MU_FAST_CONST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<uint16_t, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_IMPULSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_IMPULSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_CONST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, LP_MU_FAST_CONST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(fit_mudisp_kernel<int32_t, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaGetLastError();
-    }
+    for (int ct = 0; ct < 2; ct++)
+        for (int cl = 0; cl < 2; cl++)
+            for (int v = 0; v < 5; v++) {
+                cudaFuncSetAttribute((const void *)fit_kernel(ct != 0, v, cl != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)fit_smem_bytes(cl != 0));
+                cudaFuncAttributes fa;
+                cudaFuncGetAttributes(&fa, (const void *)fit_kernel(ct != 0, v, cl != 0));   // forces the module load
+            }
+    cudaGetLastError();
     const char *e = getenv("LPB200_NO_TABLE");
     if (e && atoi(e)) c->use_table = 0;
     e = getenv("LPB200_CTAS_PER_SM");
     if (e && atoi(e) > 0) c->ctas_per_sm = atoi(e);
     e = getenv("LPB200_NO_FASTPATH");
     if (e && atoi(e)) c->no_fastpath = 1;
+    e = getenv("LPB200_CLUSTER");
+    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) c->cluster = atoi(e);
     return c;
 }
 
@@ -791,6 +808,10 @@ struct FitJob {
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     uint64_t ole = 0, fn_evals = 0;
+    // optional per-item outputs (lpb200_fit_mudisp_items): [n_items][n] / [n_items]
+    double *items_theta0 = nullptr, *items_theta = nullptr, *items_ll = nullptr;
+    int32_t *items_conv = nullptr;
+    uint32_t *items_evals = nullptr;
     ~FitJob() {
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
@@ -838,11 +859,46 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     CK(cudaMemcpyAsync(J.d_theta0.p, J.theta0.data(), sizeof(double) * J.theta0.size(), cudaMemcpyHostToDevice, J.stream));
     CK(cudaMemsetAsync(J.d_queue.p, 0, sizeof(int), J.stream));
     const int threads = fit_threads(N);
-    // persistent CTAs: as many as stay resident (64 registers per thread; shared memory allows 4 per SM)
-    const int smem_limit = (int)((227 * 1024) / (sizeof(FitShared) + 1024));
+    // CTAs per work item: long rows are evaluated by a thread-block cluster, which divides the duration of an item
+    // -- and with it the item-length tail of the dynamic queue -- by the cluster size; the result does not depend
+    // on it (virtual-warp summation order, lp_kernels.cuh).  Short rows stay with one CTA per item: the cluster
+    // barrier per evaluation (~0.2 us) would show against a 20-40 us pass.
+    int cluster = ctx->cluster;
+    if (cluster == 0) cluster = (N >= 65536) ? 4 : (N >= 32768 ? 2 : 1);
+    if (threads != LP_FIT_THREADS) cluster = 1;
+    const bool cl = cluster > 1;
+    const size_t smem = fit_smem_bytes(cl);
+    // persistent CTAs: as many as stay resident (64 registers per thread; shared memory allows 3 per SM)
+    const int smem_limit = (int)((227 * 1024) / (smem + 1024));
     const int per_sm = std::max(1, std::min(ctx->ctas_per_sm * (LP_FIT_THREADS / threads), smem_limit));
-    const int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * per_sm);
-    J.grid = grid;
+    // specialised kernels for the hot configurations, generic kernel otherwise
+    const bool fast = !ctx->no_fastpath && lp_disp_is_scalar(D, M) && D.n_conf_mu == 0 &&
+                      (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE) &&
+                      (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
+    const int variant = !fast ? 0 : (M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) + (M.drop_model == LPB200_DROP_LOGISTIC ? 1 : 0);
+    FitKernelFn kernel = fit_kernel(ctx->is_u16, variant, cl);
+    CK(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * per_sm);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = J.stream;
+    if (cl) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(cluster);
+        int resident = 0;   // clusters that can be co-resident (GPC boundaries count)
+        CK(cudaOccupancyMaxActiveClusters(&resident, (const void *)kernel, &cfg));
+        resident = std::min(resident, ctx->sm_count * per_sm / cluster);
+        grid = cluster * (int)std::max<size_t>(1, std::min<size_t>(J.n_items, (size_t)std::max(resident, 1)));
+    }
+    cfg.gridDim = dim3(grid);
+    J.grid = grid / cluster;
     FitArgs A{};
     A.D = D;
     A.M = M;
@@ -860,40 +916,12 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     A.evals_out = J.d_evals.p;
     A.use_table = ctx->use_table;
     if ((rc = setup_drop(ctx, M, J.p, grid, A, J.B, J.stream))) return rc;
-    const size_t smem = sizeof(FitShared);
     CK(cudaEventRecord(J.e0, J.stream));
-    // specialised kernels for the hot configurations, generic kernel otherwise
-    const bool fast = !ctx->no_fastpath && lp_disp_is_scalar(D, M) && D.n_conf_mu == 0 &&
-                      (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE) &&
-                      (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
-#define LP_LAUNCH_FIT(KERNEL)                                                                               \
-    do {                                                                                                    \
-        CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        KERNEL<<<grid, threads, smem, J.stream>>>(A);                                                      \
-    } while (0)
-#define LP_LAUNCH_FIT_CT(CT)                                                                                \
-    do {                                                                                                    \
-        if (fast) {                                                                                         \
-            const bool zinb = M.drop_model == LPB200_DROP_LOGISTIC;                                         \
-            if (M.mu_model == LPB200_MU_IMPULSE) {                                                          \
-                if (zinb) LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, true>));                 \
-                else LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, false>));                     \
-            } else {                                                                                        \
-                if (zinb) LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_CONST, true>));                   \
-                else LP_LAUNCH_FIT((fit_mudisp_kernel<CT, LP_MU_FAST_CONST, false>));                       \
-            }                                                                                               \
-        } else {                                                                                            \
-            LP_LAUNCH_FIT((fit_mudisp_kernel<CT, -1, false>));                                              \
-        }                                                                                                   \
-    } while (0)
-    if (ctx->is_u16) LP_LAUNCH_FIT_CT(uint16_t);
-    else LP_LAUNCH_FIT_CT(int32_t);
-#undef LP_LAUNCH_FIT_CT
-#undef LP_LAUNCH_FIT
+    CK(cudaLaunchKernelEx(&cfg, kernel, A));
     if (getenv("LPB200_DEBUG"))
-        fprintf(stderr, "[lpb200] fit_mudisp: %s kernel (%s counts), mu=%d drop=%d items=%zu grid=%d threads=%d smem=%zu\n",
+        fprintf(stderr, "[lpb200] fit_mudisp: %s kernel (%s counts), mu=%d drop=%d items=%zu grid=%d threads=%d cluster=%d smem=%zu\n",
                 fast ? "specialised" : "generic", ctx->is_u16 ? "u16" : "i32", M.mu_model, M.drop_model, J.n_items, grid,
-                threads, smem);
+                threads, cluster, smem);
     CK(cudaGetLastError());
     CK(cudaEventRecord(J.e1, J.stream));
     ctx->stats.launches++;
@@ -932,6 +960,11 @@ static int fit_collect(lpb200_ctx *ctx, FitJob &J, float *kernel_ms) {
         fprintf(stderr, "[lpb200] fit_mudisp: %zu items, %.0f evaluations/item (max %u), kernel %.1f ms, queue balance %.3f\n",
                 n_items, total / n_items, longest, ms, total / J.grid / makespan);
     }
+    if (J.items_theta0) memcpy(J.items_theta0, J.theta0.data(), sizeof(double) * J.theta0.size());
+    if (J.items_theta) memcpy(J.items_theta, theta_out.data(), sizeof(double) * theta_out.size());
+    if (J.items_ll) memcpy(J.items_ll, ll_items.data(), sizeof(double) * n_items);
+    if (J.items_conv) memcpy(J.items_conv, conv_items.data(), sizeof(int32_t) * n_items);
+    if (J.items_evals) memcpy(J.items_evals, evals.data(), sizeof(uint32_t) * n_items);
     bool nonfinite = false;
     for (int i = 0; i < G; i++) {
         int best = 0;
@@ -966,13 +999,20 @@ static int fit_collect(lpb200_ctx *ctx, FitJob &J, float *kernel_ms) {
 }
 
 static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p, const lpb200_control *c, double *ll,
-                           int32_t *conv) {
+                           int32_t *conv, const FitJob *items = nullptr) {
     FitJob J;
     J.M = M;
     J.p = p;
     J.ll = ll;
     J.conv = conv;
     J.stream = ctx->stream;
+    if (items) {
+        J.items_theta0 = items->items_theta0;
+        J.items_theta = items->items_theta;
+        J.items_ll = items->items_ll;
+        J.items_conv = items->items_conv;
+        J.items_evals = items->items_evals;
+    }
     int rc = fit_launch(ctx, J, c);
     if (rc) return rc;
     float ms = 0.f;
@@ -991,6 +1031,27 @@ extern "C" int lpb200_fit_mudisp(lpb200_ctx *ctx, const lpb200_model *m, lpb200_
     if ((rc = check_params(ctx, M, p, true))) return rc;
     lpb200_control tmp;
     return fit_mudisp_impl(ctx, M, p, control_or_default(c, tmp), ll, conv);
+}
+
+extern "C" int lpb200_fit_mudisp_items(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c,
+                                       double *ll, int32_t *conv, int32_t *n_starts, int32_t *n_theta, double *theta0,
+                                       double *theta, double *ll_items, int32_t *conv_items, uint32_t *evals_items) {
+    int rc = require_ready(ctx);
+    if (rc) return rc;
+    DevModel M;
+    if (!m || !ll || !conv || !n_starts || !n_theta) return set_err(ctx, LPB200_E_ARG, "fit_mudisp_items: NULL argument");
+    if ((rc = make_model(ctx, m, M))) return rc;
+    if ((rc = check_params(ctx, M, p, true))) return rc;
+    *n_starts = (M.mu_model == LPB200_MU_IMPULSE) ? 3 : 1;
+    *n_theta = M.n_theta;
+    FitJob items;
+    items.items_theta0 = theta0;
+    items.items_theta = theta;
+    items.items_ll = ll_items;
+    items.items_conv = conv_items;
+    items.items_evals = evals_items;
+    lpb200_control tmp;
+    return fit_mudisp_impl(ctx, M, p, control_or_default(c, tmp), ll, conv, &items);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1593,6 +1654,24 @@ extern "C" int lpb200_div_probe(lpb200_ctx *ctx, const double *a, const double *
     ctx->stats.launches++;
     CK(cudaMemcpyAsync(quot_out, dq.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(rcp_out, dr.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lpb200_rcp64h_probe(lpb200_ctx *ctx, const int32_t *hi, int n, int32_t lo, int32_t *out_hi, int32_t *out_lo) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (!hi || !out_hi || !out_lo || n <= 0) return set_err(ctx, LPB200_E_ARG, "rcp64h_probe: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf<int32_t> dh, doh, dol;
+    CK(dh.alloc(n));
+    CK(doh.alloc(n));
+    CK(dol.alloc(n));
+    CK(cudaMemcpyAsync(dh.p, hi, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    rcp64h_probe_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(dh.p, n, lo, doh.p, dol.p);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    CK(cudaMemcpyAsync(out_hi, doh.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_lo, dol.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -20,12 +20,8 @@
 #include "lp_bfgs.cuh"
 #include "lp_model.cuh"
 #include "lp_exact.cuh"
+#include "lp_eval.cuh"
 
-#define LP_KC 32          // evaluation points per chunk (one warp row)
-#ifndef LP_TAB
-#define LP_TAB 1024       // entries of one (x, phi) table
-#endif
-#define LP_NTAB 3         // tables per pass: base phi, phi + eps, phi - eps
 // Threads of a fit CTA (one CTA works on one (gene, start) item) and CTAs per SM: 32 warps per SM either
 // way (register cap 64).  512 x 2 instead of 256 x 4 halves the duration of an item and with it the
 // item-length tail of the dynamic queue (balance 0.86 -> 0.96 at 15 000 items, -4 % at 1 184 genes,
@@ -34,6 +30,7 @@
 #define LP_FIT_THREADS 512
 #endif
 #define LP_MAX_WARPS (LP_FIT_THREADS / 32)
+#define LP_MAX_CLUSTER 4  // CTAs that evaluate one item together (LP_VW / LP_MAX_WARPS)
 #define LP_PI_NP 8        // max drop-out parameters per cell (1 + ofMu + LPB200_MAX_PI_PRED)
 #define LP_PI_KP 16       // points per cell per round (2q)
 #ifndef LP_FAST_MINBLOCKS
@@ -87,34 +84,135 @@ struct FitArgs {
     int use_table;
 };
 
-struct FitShared {
+// Shared memory of a fit CTA.  CL: the CTA is one of a thread-block cluster that evaluates an item together;
+// the partial sums are then double-buffered (one cluster barrier per evaluation instead of two).
+template <bool CL>
+struct FitSharedT {
     BfgsState<LPB200_MAX_PARAMS> st;
     PointNat pts[LP_KC];
     double vals[2 * LPB200_MAX_PARAMS];
-    double red[LP_KC * LP_MAX_WARPS];
+    double red[CL ? 2 : 1][LP_VW][LP_KC + 1];   // [buffer][virtual warp][point]; +1: conflict-free in both directions
     double tab[LP_NTAB][LP_TAB];
     double tab_phi[LP_NTAB];
     int tab_of_point[LP_KC];
     int item;
+    unsigned epoch;                               // evaluations done (selects the red buffer)
+};
+typedef FitSharedT<false> FitShared;
+
+__device__ __forceinline__ unsigned lp_cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned lp_cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void lp_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the double at the same shared-memory offset as `p` in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ double lp_dsmem_load(const double *p, unsigned rank) {
+    unsigned local = (unsigned)__cvta_generic_to_shared(p), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lp_dsmem_load_int(const int *p, unsigned rank) {
+    unsigned local = (unsigned)__cvta_generic_to_shared(p), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Evaluation layout.  The cells of a gene (in the order of its permutation: non-zero observations first) are
+// dealt to LP_VW = 64 VIRTUAL warps: virtual warp v, slot s takes the cells r = v cpw + s + i 64 cpw
+// (cpw = 32 / npad cells per warp iteration, npad = points padded to a power of two), each lane adds its
+// (cell, point) terms in that order, the slots of a virtual warp are combined by xor shuffles and the 64
+// virtual warps are added in index order.  Which PHYSICAL warp runs a virtual warp does not matter, so the sum
+// -- and with it every decision of the optimiser -- is the same for a CTA of 128 or 512 threads and for a
+// cluster of 1, 2 or 4 CTAs working on the item together (physical warp p of P takes v = p, p + P, ...).
+// The host mirror (tests/csrc/mirror_harness.cpp) restates exactly this order.
+// ---------------------------------------------------------------------------------------------------------
+// Lane policies: the (cell, point) term of the specialised and of the generic evaluator.
+template <typename CT, int MU, bool ZINB>
+struct FastLane {
+    FastPoint F;
+    const double *tabp, *tt, *sf, *pi_ptr, *l1m_ptr;
+    const CT *row;
+    int tab_len, nnz;
+    template <typename SH>
+    __device__ __forceinline__ void setup(const FitArgs &A, SH &S, const CT *row_, int gene, int k, int tab_len_,
+                                          const double *pi_ptr_, const double *l1m_ptr_) {
+        lp_fast_point<MU>(S.pts[k], F);
+        tab_len = tab_len_;
+        tabp = tab_len > 0 ? S.tab[S.tab_of_point[k]] : nullptr;
+        tt = A.D.t;
+        sf = A.D.sf;
+        pi_ptr = pi_ptr_;
+        l1m_ptr = l1m_ptr_;
+        row = row_;
+        nnz = A.C.nnz[gene];
+    }
+    __device__ __forceinline__ double term(int r, int j) const {
+        const int x = (r < nnz) ? lp_load_count(row, j) : 0;
+        return lp_fast_cell<MU, ZINB>(F, x, j, tt, sf, pi_ptr, l1m_ptr, tabp, tab_len);
+    }
+};
+template <typename CT>
+struct GenericLane {
+    const FitArgs *A;
+    const PointNat *P;
+    const double *tabp, *pi_ptr, *l1m_ptr;
+    const CT *row;
+    double phi_s, logphi_s;
+    int tab_len, gene;
+    template <typename SH>
+    __device__ __forceinline__ void setup(const FitArgs &A_, SH &S, const CT *row_, int gene_, int k, int tab_len_,
+                                          const double *pi_ptr_, const double *l1m_ptr_) {
+        A = &A_;
+        P = &S.pts[k];
+        phi_s = 1.0;
+        logphi_s = 0.0;
+        tabp = nullptr;
+        tab_len = tab_len_;
+        if (lp_disp_is_scalar(A_.D, A_.M)) {
+            phi_s = P->disp[0];
+            logphi_s = lp_log(phi_s);
+            if (tab_len > 0) tabp = S.tab[S.tab_of_point[k]];
+        }
+        pi_ptr = pi_ptr_;
+        l1m_ptr = l1m_ptr_;
+        row = row_;
+        gene = gene_;
+    }
+    __device__ __forceinline__ double term(int r, int j) const {
+        const int x = lp_load_count(row, j);
+        const double s = A->D.sf ? A->D.sf[j] : 1.0;
+        double pf = 0.0, l1 = 0.0;
+        if (pi_ptr) {
+            pf = pi_ptr[j];
+            l1 = l1m_ptr[j];
+        }
+        return lp_cell_ll(A->D, A->M, *P, A->drop, gene, j, x, s, pf, l1, phi_s, logphi_s, tabp, tab_len);
+    }
 };
 
 // Evaluate nk (<= LP_KC) points S.pts[0..nk) for one gene; results in out_vals[0..nk).
-// All threads of the CTA must call this (it contains __syncthreads()).
-template <typename CT>
-__device__ void lp_eval_points(const FitArgs &A, FitShared &S, const CT *row, int gene, int xmax, int nk,
-                               int ntabs, double *out_vals, const double *pi_ptr, const double *l1m_ptr) {
-    const DevDesign &D = A.D;
-    const DevModel &M = A.M;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int N = D.N;
-    const bool scalar_phi = lp_disp_is_scalar(D, M);
-
+// All threads of the CTA (CL: of every CTA of the cluster) must call this.
+template <bool CL, typename LANE, typename CT, typename SH>
+__device__ void lp_eval_points(const FitArgs &A, SH &S, const CT *row, int gene, int xmax, int nk, int ntabs,
+                               bool tables_allowed, double *out_vals, const double *pi_ptr, const double *l1m_ptr) {
+    const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const unsigned crank = CL ? lp_cluster_ctarank() : 0u, csize = CL ? lp_cluster_nctarank() : 1u;
+    const int pwarp = (int)crank * nwarps + (tid >> 5), P = (int)csize * nwarps;   // physical warp of the cluster
     // (x, phi)-only part of dnbinom tabulated per distinct phi when that is cheaper than N x nk
-    int tab_len = 0;
-    if (scalar_phi && A.use_table && ntabs > 0) {
-        int want = min(xmax + 1, LP_TAB);
-        if ((long long)ntabs * want * 2 <= (long long)nk * N) tab_len = want;
-    }
+    const int tab_len = tables_allowed ? lp_table_len(A.use_table, ntabs, xmax, nk, A.D.N) : 0;
     if (tab_len > 0) {
         for (int e = tid; e < ntabs * tab_len; e += blockDim.x) {
             int tsel = e / tab_len, x = e - tsel * tab_len;
@@ -122,136 +220,50 @@ __device__ void lp_eval_points(const FitArgs &A, FitShared &S, const CT *row, in
         }
     }
     __syncthreads();
-
     int npad = 1;
     while (npad < nk) npad <<= 1;
     const int cpw = 32 / npad;            // cells per warp per iteration
     const int k = lane & (npad - 1);      // this lane's point
     const int slot = lane / npad;
     const bool active = k < nk;
-    const PointNat &P = S.pts[active ? k : 0];
-    double phi_s = 1.0, logphi_s = 0.0;
-    const double *tabp = nullptr;
-    if (scalar_phi) {
-        phi_s = P.disp[0];
-        logphi_s = lp_log(phi_s);
-        if (tab_len > 0) tabp = S.tab[S.tab_of_point[active ? k : 0]];
-    }
-    double acc = 0.0;
-    const int stride = nwarps * cpw;
+    const int buf = CL ? (int)(S.epoch & 1u) : 0;
+    LANE L;
+    L.setup(A, S, row, gene, active ? k : 0, tab_len, pi_ptr, l1m_ptr);
     const uint32_t *perm = A.C.perm + (size_t)gene * A.C.pitch;
     const int nobs = A.C.nobs[gene];
-    for (int r = warp * cpw + slot; r < nobs; r += stride) {
-        if (!active) continue;
-        const int j = (int)perm[r];
-        int x = lp_load_count(row, j);
-        double s = D.sf ? D.sf[j] : 1.0;
-        double pf = 0.0, l1 = 0.0;
-        if (pi_ptr) {
-            pf = pi_ptr[j];
-            l1 = l1m_ptr[j];
+    const int stride = LP_VW * cpw;
+    for (int v = pwarp; v < LP_VW; v += P) {
+        double acc = 0.0;
+        if (active) {
+            int r = v * cpw + slot;
+            int j = (r < nobs) ? (int)perm[r] : 0;
+            for (; r < nobs; r += stride) {
+                // the next cell index is fetched one iteration ahead: the gathers of the term (count, pseudotime,
+                // drop-out rate) then hang off a register instead of a second dependent L2 access
+                const int r_next = r + stride;
+                const int j_next = (r_next < nobs) ? (int)perm[r_next] : 0;
+                acc += L.term(r, j);
+                j = j_next;
+            }
         }
-        acc += lp_cell_ll(D, M, P, A.drop, gene, j, x, s, pf, l1, phi_s, logphi_s, tabp, tab_len);
+        // combine the cell slots of the virtual warp (fixed order => deterministic)
+        for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane < npad && lane < nk) S.red[buf][v][lane] = acc;
     }
-    // combine the cell slots of the warp, then the warps (fixed order => deterministic)
-    for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane < npad && lane < nk) S.red[lane * LP_MAX_WARPS + warp] = acc;
-    __syncthreads();
-    if (tid < nk) {
+    if (CL) lp_cluster_sync();
+    else __syncthreads();
+    if (tid < nk) {   // the 64 virtual warps in index order; virtual warp v lives in CTA (v mod P) / nwarps
         double s = 0.0;
-        for (int w = 0; w < nwarps; w++) s += S.red[tid * LP_MAX_WARPS + w];
+        if (CL) {
+#pragma unroll 8
+            for (int v = 0; v < LP_VW; v++) s += lp_dsmem_load(&S.red[buf][v][tid], (unsigned)((v % P) / nwarps));
+        } else {
+#pragma unroll 8
+            for (int v = 0; v < LP_VW; v++) s += S.red[0][v][tid];
+        }
         out_vals[tid] = s;
     }
-    __syncthreads();
-}
-
-// Specialised evaluator for the hot configurations (BASELINE configs C1-C3): constant or impulse
-// mean, one scalar dispersion per gene, no mean confounders, drop-out "none" or gene-wise fixed
-// ("logistic").  Same arithmetic as lp_cell_ll -- operation for operation, so results are
-// bit-identical to the generic path -- but the lane's point lives in registers and the dead model
-// branches are gone (the generic kernel is ~13k SASS instructions, far beyond the I-cache).
-__device__ __noinline__ double lp_nb_xphi_part_cold(double x, double phi) { return lp_nb_xphi_part(x, phi); }
-#define LP_MU_FAST_CONST 0
-#define LP_MU_FAST_IMPULSE 1
-template <typename CT, int MU, bool ZINB>
-__device__ void lp_eval_points_fast(const FitArgs &A, FitShared &S, const CT *row, int gene, int xmax, int nk, int ntabs,
-                                    double *out_vals, const double *pi_ptr, const double *l1m_ptr) {
-    const DevDesign &D = A.D;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int N = D.N;
-    int tab_len = 0;
-    if (A.use_table && ntabs > 0) {
-        int want = min(xmax + 1, LP_TAB);
-        if ((long long)ntabs * want * 2 <= (long long)nk * N) tab_len = want;
-    }
-    if (tab_len > 0) {
-        for (int e = tid; e < ntabs * tab_len; e += blockDim.x) {
-            int tsel = e / tab_len, x = e - tsel * tab_len;
-            S.tab[tsel][x] = (x == 0) ? 0.0 : lp_nb_xphi_part((double)x, S.tab_phi[tsel]);
-        }
-    }
-    __syncthreads();
-    int npad = 1;
-    while (npad < nk) npad <<= 1;
-    const int cpw = 32 / npad;
-    const int k = lane & (npad - 1);
-    const int slot = lane / npad;
-    const bool active = k < nk;
-    const PointNat &P = S.pts[active ? k : 0];
-    const double phi = P.disp[0];
-    const double logphi = lp_log(phi);
-    const double p0 = P.mu[0];
-    double b2 = 0, h0 = 0, h1 = 0, h2 = 0, t1 = 0, t2 = 0, inv_h1 = 0;
-    if (MU == LP_MU_FAST_IMPULSE) {
-        b2 = P.mu[1]; h0 = P.mu[2]; h1 = P.mu[3]; h2 = P.mu[4]; t1 = P.mu[5]; t2 = P.mu[6];
-        inv_h1 = 1.0 / h1;
-    }
-    const double *tabp = tab_len > 0 ? S.tab[S.tab_of_point[active ? k : 0]] : nullptr;
-    const double *sf = D.sf;
-    const double *tt = D.t;
-    double acc = 0.0;
-    const int stride = nwarps * cpw;
-    const uint32_t *perm = A.C.perm + (size_t)gene * A.C.pitch;
-    const int nobs = A.C.nobs[gene], nnz = A.C.nnz[gene];
-    if (active) {
-        int r = warp * cpw + slot;
-        int j = (r < nobs) ? (int)perm[r] : 0;
-        for (; r < nobs; r += stride) {
-            // the next cell index is fetched one iteration ahead: the gathers below (count, pseudotime,
-            // drop-out rate) then hang off a register instead of a second dependent L2 access
-            const int r_next = r + stride;
-            const int j_next = (r_next < nobs) ? (int)perm[r_next] : 0;
-            const int x = (r < nnz) ? lp_load_count(row, j) : 0;
-            double mu;
-            if (MU == LP_MU_FAST_IMPULSE) {
-                const double t = tt[j];
-                double s1, s2;
-                lp_sigmoid_pair(-p0 * (t - t1), b2 * (t - t2), s1, s2);
-                mu = inv_h1 * (h0 + (h1 - h0) * s1) * (h2 + (h1 - h2) * s2);
-            } else {
-                mu = p0;
-            }
-            const double mus = sf ? mu * sf[j] : mu;
-            double v;
-            if (x == 0) {
-                v = ZINB ? lp_ll_zero_zinb(mus, phi, pi_ptr[j]) : lp_ll_zero_nb(mus, phi, logphi);
-            } else {
-                const double xd = (double)x;
-                const double xphi = (x < tab_len) ? tabp[x] : lp_nb_xphi_part_cold(xd, phi);  // cold: keeps lgamma out of the loop body
-                v = lp_ll_nonzero(xd, xphi, mus, phi, ZINB ? l1m_ptr[j] : 0.0);
-            }
-            acc += v;
-            j = j_next;
-        }
-    }
-    for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane < npad && lane < nk) S.red[lane * LP_MAX_WARPS + warp] = acc;
-    __syncthreads();
-    if (tid < nk) {
-        double s = 0.0;
-        for (int w = 0; w < nwarps; w++) s += S.red[tid * LP_MAX_WARPS + w];
-        out_vals[tid] = s;
-    }
+    if (tid == 0) S.epoch++;
     __syncthreads();
 }
 
@@ -279,21 +291,33 @@ __device__ void lp_fixed_pi(const FitArgs &A, int gene, const double *&pi_ptr, c
     l1m_ptr = ls;
 }
 
-// MU = -1: generic evaluator (any model); MU = LP_MU_FAST_*: specialised evaluator, ZINB selects
-// the fixed-drop-out ZINB terms over the NB terms.
-template <typename CT, int MU, bool ZINB>
+// MU = -1: generic evaluator (any model); MU = LP_MU_FAST_*: specialised evaluator (constant or impulse mean, one
+// scalar dispersion per gene, no mean confounders, drop-out "none" or gene-wise fixed "logistic": BASELINE
+// configs C1-C3; same arithmetic as lp_cell_ll operation for operation -- bit-identical to the generic path --
+// but the lane's point lives in registers and the dead model branches are gone; the generic kernel is ~13k SASS
+// instructions, far beyond the I-cache), ZINB selects the fixed-drop-out ZINB terms over the NB terms.
+// CL: launched as thread-block clusters; the CTAs of a cluster take one (gene, start) item together, each
+// running the optimiser state machine redundantly on the same all-cluster sums (item-length tail / cluster size).
+template <typename CT, int MU, bool ZINB, bool CL>
 __global__ void __launch_bounds__(LP_FIT_THREADS, (MU >= 0) ? LP_FAST_MINBLOCKS : LP_GENERIC_MINBLOCKS)
 fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
     extern __shared__ __align__(16) unsigned char lp_smem[];
-    FitShared &S = *reinterpret_cast<FitShared *>(lp_smem);
+    typedef FitSharedT<CL> SH;
+    SH &S = *reinterpret_cast<SH *>(lp_smem);
     const DevDesign &D = A.D;
     const DevModel &M = A.M;
     const int tid = threadIdx.x;
     const int n = M.n_theta;
     const bool scalar_phi = lp_disp_is_scalar(D, M);
+    const unsigned crank = CL ? lp_cluster_ctarank() : 0u;
+    if (tid == 0) S.epoch = 0;
 
     for (;;) {
-        if (tid == 0) S.item = atomicAdd(A.queue, 1);
+        if (tid == 0 && crank == 0) S.item = atomicAdd(A.queue, 1);
+        if (CL) {   // the leader's item for every CTA of the cluster (the barrier of the item's first evaluation
+            lp_cluster_sync();                                   // orders this read before the leader's next write)
+            if (tid == 0 && crank != 0) S.item = lp_dsmem_load_int(&S.item, 0u);
+        }
         __syncthreads();
         const int item = S.item;
         if (item >= A.n_items) break;
@@ -312,40 +336,35 @@ fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
             for (int base = 0; base < total; base += LP_KC) {
                 const int kc = min(LP_KC, total - base);
                 if (tid < kc) {
-                    double th[LPB200_MAX_PARAMS];
-                    for (int i = 0; i < n; i++) th[i] = S.st.b[i];
-                    int tsel = 0;
-                    if (req == LP_REQ_GRAD) {
-                        int kk = base + tid, c = bfgs_grad_coord(kk);
-                        th[c] = bfgs_grad_point(S.st.b[c], kk, A.ndeps);
-                        if (scalar_phi && c == 0) tsel = 1 + (kk & 1);  // the dispersion coordinate
-                    }
-                    lp_unpack_theta(D, M, th, S.pts[tid]);
+                    const int tsel = lp_request_point(D, M, S.st.b, n, req, base + tid, A.ndeps, scalar_phi, S.pts[tid]);
                     S.tab_of_point[tid] = tsel;
                     if (scalar_phi) S.tab_phi[tsel] = S.pts[tid].disp[0];
                 }
                 if (tid == LP_KC && scalar_phi && req == LP_REQ_GRAD) {
                     // base phi for the points that do not move the dispersion coordinate
-                    S.tab_phi[0] = lp_clamp(exp(S.st.b[0]), LP_CLAMP_LO, LP_CLAMP_HI);
+                    S.tab_phi[0] = lp_base_phi(S.st.b);
                 }
                 __syncthreads();
-                const int ntabs = (req == LP_REQ_F) ? 1 : (base == 0 ? 3 : 1);
+                const int ntabs = lp_request_ntabs(req, base);
                 if constexpr (MU >= 0)
-                    lp_eval_points_fast<CT, MU, ZINB>(A, S, row, gene, xmax, kc, ntabs, S.vals + base, pi_ptr, l1m_ptr);
+                    lp_eval_points<CL, FastLane<CT, MU, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
                 else
-                    lp_eval_points<CT>(A, S, row, gene, xmax, kc, ntabs, S.vals + base, pi_ptr, l1m_ptr);
+                    lp_eval_points<CL, GenericLane<CT>>(A, S, row, gene, xmax, kc, ntabs, scalar_phi, S.vals + base, pi_ptr, l1m_ptr);
             }
             if (tid == 0) bfgs_advance(S.st, S.vals);
             __syncthreads();
         }
-        if (tid < n) A.theta_out[(size_t)item * n + tid] = S.st.b[tid];
-        if (tid == 0) {
-            A.ll_out[item] = (S.st.fail == 1001) ? NAN : -S.st.Fmin;
-            A.conv_out[item] = S.st.fail;
-            A.evals_out[item] = S.st.evals;
+        if (crank == 0) {
+            if (tid < n) A.theta_out[(size_t)item * n + tid] = S.st.b[tid];
+            if (tid == 0) {
+                A.ll_out[item] = (S.st.fail == 1001) ? NAN : -S.st.Fmin;
+                A.conv_out[item] = S.st.fail;
+                A.evals_out[item] = S.st.evals;
+            }
         }
         __syncthreads();
     }
+    if (CL) lp_cluster_sync();   // no CTA leaves while a neighbour may still read its shared memory
 }
 
 // evalLogLikMatrix: one CTA per gene (grid-stride), stored natural-scale parameters
@@ -356,6 +375,7 @@ eval_ll_kernel(const __grid_constant__ FitArgs A) {
     FitShared &S = *reinterpret_cast<FitShared *>(lp_smem);
     const DevModel &M = A.M;
     const int n_nat = lp_n_nat(M);
+    if (threadIdx.x == 0) S.epoch = 0;
     for (int gene = blockIdx.x; gene < A.D.G; gene += gridDim.x) {
         const CT *row = reinterpret_cast<const CT *>(A.C.ptr) + (size_t)gene * A.C.pitch;
         const double *pi_ptr, *l1m_ptr;
@@ -366,7 +386,7 @@ eval_ll_kernel(const __grid_constant__ FitArgs A) {
             S.tab_phi[0] = S.pts[0].disp[0];
         }
         __syncthreads();
-        lp_eval_points<CT>(A, S, row, gene, A.C.xmax[gene], 1, 1, S.vals, pi_ptr, l1m_ptr);
+        lp_eval_points<false, GenericLane<CT>>(A, S, row, gene, A.C.xmax[gene], 1, 1, lp_disp_is_scalar(A.D, M), S.vals, pi_ptr, l1m_ptr);
         if (threadIdx.x == 0) A.ll_out[gene] = S.vals[0];
         __syncthreads();
     }
@@ -615,6 +635,7 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
             const double lmu = (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) ? log(mu) : 0.0;
             double core;  // theta-independent part
             if (x == 0) core = exp(phi * log(phi / (phi + mus)));
+            else if (lp_nb_small_x((double)x, phi)) core = lp_dnbinom_small_x((double)x, mus, phi);
             else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
 #pragma unroll
             for (int k = 0; k < LP_PI_KP; k++) {
@@ -795,6 +816,7 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
                 const double lmu = (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) ? log(mu) : 0.0;
                 double core;
                 if (x == 0) core = exp(phi * log(phi / (phi + mus)));
+                else if (lp_nb_small_x((double)x, phi)) core = lp_dnbinom_small_x((double)x, mus, phi);
                 else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
 #pragma unroll
                 for (int k = 0; k < LP_PI_KP; k++) {
@@ -1068,5 +1090,17 @@ __global__ void div_probe_kernel(const double *a, const double *b, int n, int us
             q[k] = lp_div<true>(a[k], b[k]);
             r[k] = lp_rcp<true>(b[k]);
         }
+    }
+}
+
+// MUFU.RCP64H (rcp.approx.ftz.f64) of the double (hi, lo): upper and lower result words.  The logarithm of
+// lp_libm.cuh is the only routine whose bits depend on this seed (the divisions are correctly rounded); the
+// dump of all 2^20 mantissas (scripts/dump_rcp64h.py -> tests/golden/rcp64h.npz) lets the host mirror of the
+// fit kernel reproduce the device logarithm bit for bit.
+__global__ void rcp64h_probe_kernel(const int32_t *hi, int n, int32_t lo, int32_t *out_hi, int32_t *out_lo) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double r = lp_rcp_approx(__hiloint2double(hi[k], lo));
+        out_hi[k] = __double2hiint(r);
+        out_lo[k] = __double2loint(r);
     }
 }

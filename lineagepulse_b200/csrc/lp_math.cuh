@@ -62,6 +62,29 @@ __constant__ double lp_sferr_dev[31] = LP_SFERR_VALUES;
 __constant__ double lp_odd_recip_dev[9] = LP_ODD_RECIP_VALUES;
 #endif
 
+// log1p and lgamma of the table-building code.  Not the CUDA library's: own routines over lp_log and IEEE
+// operations only, so that every operation of the fit path is reproducible on the host (the mirror of
+// tests/csrc/mirror_harness.cpp, which the GPU tests compare with the kernels bit for bit).
+// log1p(a) by the classical correction log(u) a / (u - 1), u = fl(1 + a): a few ulp for every a > -1.
+LP_HD double lp_log1p(double a) {
+    const double u = 1.0 + a;
+    if (u == 1.0) return a;
+    return lp_log(u) * (a / (u - 1.0));
+}
+// lgamma(z) for 1 < z <= 16: the recurrence lifts the argument to w >= 17, where six Stirling terms leave less
+// than 1e-17; absolute error <= 2e-14 against 40-digit arithmetic over the whole interval (as good as the lgamma
+// difference R's stirlerr forms with it: the result is a difference of numbers of size ~30).
+LP_HD double lp_lgamma_1_16(double z) {
+    double prod = 1.0, w = z;
+    while (w < 17.0) {
+        prod *= w;
+        w += 1.0;
+    }
+    const double iw = 1.0 / w, iw2 = iw * iw;
+    const double ser = iw * (1.0 / 12.0 - iw2 * (1.0 / 360.0 - iw2 * (1.0 / 1260.0 - iw2 * (1.0 / 1680.0 - iw2 * (1.0 / 1188.0 - iw2 * (691.0 / 360360.0))))));
+    return (w - 0.5) * lp_log(w) - w + LP_LN_SQRT_2PI + ser - lp_log(prod);
+}
+
 // stirlerr(n) = log(n!) - log(sqrt(2 pi n) (n/e)^n)
 LP_HD double lp_stirlerr(double n) {
     if (n <= 15.0) {
@@ -73,7 +96,7 @@ LP_HD double lp_stirlerr(double n) {
             return lp_sferr_host[(int)nn];
 #endif
         }
-        return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - LP_LN_SQRT_2PI;
+        return lp_lgamma_1_16(n + 1.0) - (n + 0.5) * lp_log(n) + n - LP_LN_SQRT_2PI;
     }
     const double S0 = 0.083333333333333333333, S1 = 0.00277777777777777777778, S2 = 0.00079365079365079365079365,
                  S3 = 0.000595238095238095238095238, S4 = 0.0008417508417508417508417508;
@@ -133,7 +156,7 @@ LP_HD bool lp_div_safe(double mu, double phi) { return mu > 1e-100 && mu < 1e100
 LP_HD double lp_nb_xphi_part(double x, double phi) {
     double n = x + phi;
     double xm = n - phi;
-    double lf = LP_LN_2PI + lp_log(phi) + log1p(-phi / n);
+    double lf = LP_LN_2PI + lp_log(phi) + lp_log1p(-phi / n);
     return lp_log(phi / (phi + x)) + (lp_stirlerr(n) - lp_stirlerr(phi) - lp_stirlerr(xm)) - 0.5 * lf;
 }
 
@@ -147,6 +170,22 @@ LP_HD double lp_nb_mu_part_t(double x, double mu, double phi) {
 }
 LP_HD double lp_nb_mu_part(double x, double mu, double phi) {
     return lp_div_safe(mu, phi) ? lp_nb_mu_part_t<true>(x, mu, phi) : lp_nb_mu_part_t<false>(x, mu, phi);
+}
+
+// dnbinom_mu's other branch: for x < 1e-10 * size R does not go through dbinom_raw but evaluates
+//   x log(mu / (1 + mu/size)) - mu - lgamma(x + 1) + log1p(x (x - 1) / (2 size))
+// (with log(size / (1 + size/mu)) when size < mu).  Constant and group dispersions are clamped at 1e10 and
+// x >= 1, so only products with dispersion batch factors, spline dispersions or stored parameters handed to
+// evalLogLikMatrix reach it: a cold function, tested by the callers that can see such a phi.
+LP_HD bool lp_nb_small_x(double x, double phi) { return x < 1e-10 * phi; }
+#ifdef __CUDACC__
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+double lp_dnbinom_small_x(double x, double mu, double phi) {
+    const double p = (phi < mu) ? lp_log(phi / (1.0 + phi / mu)) : lp_log(mu / (1.0 + mu / phi));
+    return x * p - mu - lgamma(x + 1.0) + lp_log1p(x * (x - 1.0) / (2.0 * phi));
 }
 
 // Non-zero observation: dnbinom(x, mu, size=phi, log) [+ log(1-pi)], floored

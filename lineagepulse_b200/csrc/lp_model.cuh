@@ -6,38 +6,39 @@
 #include "lp_math.cuh"
 
 // theta = [disp params | disp batch logs | mu params | mu batch logs]  ->  natural scale
+// (lp_exp: on the device bit-identical to the CUDA library's exp, on the host the C library's)
 LP_HD void lp_unpack_theta(const DevDesign &D, const DevModel &M, const double *th, PointNat &g) {
     int u = 0;
     if (M.disp_model == LPB200_DISP_SPLINES) {  // raw coefficients, clamp +-10 log 10
-        const double lim = 10.0 * log(10.0);
+        const double lim = 10.0 * lp_log(10.0);
         for (int k = 0; k < M.p_disp; k++) g.disp[k] = lp_clamp(th[u + k], -lim, lim);
     } else {
-        for (int k = 0; k < M.p_disp; k++) g.disp[k] = lp_clamp(exp(th[u + k]), LP_CLAMP_LO, LP_CLAMP_HI);
+        for (int k = 0; k < M.p_disp; k++) g.disp[k] = lp_clamp(lp_exp(th[u + k]), LP_CLAMP_LO, LP_CLAMP_HI);
     }
     u += M.p_disp;
     int o = 0;
     for (int c = 0; c < D.n_conf_disp; c++) {
         g.bdisp[o] = 1.0;
-        for (int b = 1; b < D.nb_disp[c]; b++) g.bdisp[o + b] = lp_clamp(exp(th[u + b - 1]), LP_CLAMP_LO, LP_CLAMP_HI);
+        for (int b = 1; b < D.nb_disp[c]; b++) g.bdisp[o + b] = lp_clamp(lp_exp(th[u + b - 1]), LP_CLAMP_LO, LP_CLAMP_HI);
         u += D.nb_disp[c] - 1;
         o += D.nb_disp[c];
     }
     if (M.mu_model == LPB200_MU_IMPULSE) {
         for (int k = 0; k < 7; k++) g.mu[k] = th[u + k];
-        for (int k = 2; k < 5; k++) g.mu[k] = exp(g.mu[k]);
+        for (int k = 2; k < 5; k++) g.mu[k] = lp_exp(g.mu[k]);
         for (int k = 0; k < 2; k++)
             if (g.mu[k] < LP_CLAMP_LO) g.mu[k] = LP_CLAMP_LO;
         for (int k = 2; k < 5; k++) g.mu[k] = lp_clamp(g.mu[k], LP_CLAMP_LO, LP_CLAMP_HI);
     } else if (M.mu_model == LPB200_MU_SPLINES) {
         for (int k = 0; k < M.p_mu; k++) g.mu[k] = lp_clamp(th[u + k], -LP_CLAMP_HI, LP_CLAMP_HI);
     } else {
-        for (int k = 0; k < M.p_mu; k++) g.mu[k] = lp_clamp(exp(th[u + k]), LP_CLAMP_LO, LP_CLAMP_HI);
+        for (int k = 0; k < M.p_mu; k++) g.mu[k] = lp_clamp(lp_exp(th[u + k]), LP_CLAMP_LO, LP_CLAMP_HI);
     }
     u += M.p_mu;
     o = 0;
     for (int c = 0; c < D.n_conf_mu; c++) {
         g.bmu[o] = 1.0;
-        for (int b = 1; b < D.nb_mu[c]; b++) g.bmu[o + b] = lp_clamp(exp(th[u + b - 1]), LP_CLAMP_LO, LP_CLAMP_HI);
+        for (int b = 1; b < D.nb_mu[c]; b++) g.bmu[o + b] = lp_clamp(lp_exp(th[u + b - 1]), LP_CLAMP_LO, LP_CLAMP_HI);
         u += D.nb_mu[c] - 1;
         o += D.nb_mu[c];
     }
@@ -154,6 +155,10 @@ LP_HD double lp_cell_ll(const DevDesign &D, const DevModel &M, const PointNat &g
         return lp_ll_zero_zinb(mus, phi, pi);
     }
     double xd = (double)x;
+    if (lp_nb_small_x(xd, phi)) {   // dnbinom_mu's x < 1e-10 * size branch (phi beyond the 1e10 clamp of a scalar dispersion)
+        double v = ((M.drop_model == LPB200_DROP_NONE) ? 0.0 : l1m) + lp_dnbinom_small_x(xd, mus, phi);
+        return (v < LP_LL_FLOOR) ? LP_LL_FLOOR : v;
+    }
     double xphi = (xphi_tab && x < tab_len) ? xphi_tab[x] : lp_nb_xphi_part(xd, phi);
     return lp_ll_nonzero(xd, xphi, mus, phi, (M.drop_model == LPB200_DROP_NONE) ? 0.0 : l1m);
 }

@@ -139,6 +139,32 @@ class Engine:
         params.sync_back()
         return dict(ll=ll, conv=conv, rc=rc)
 
+    def fit_mudisp_items(self, model, params, control=None):
+        """fit_mudisp plus every (gene, start) work item of the fit kernel (lpb200_fit_mudisp_items)."""
+        control = control or A.default_control()
+        G = self.n_genes
+        ll = np.zeros(G)
+        conv = np.zeros(G, dtype=np.int32)
+        ns, nt = C.c_int32(), C.c_int32()
+        cap = G * 3
+        theta0 = np.zeros((cap, A.MAX_PARAMS))
+        theta = np.zeros((cap, A.MAX_PARAMS))
+        ll_i = np.zeros(cap)
+        conv_i = np.zeros(cap, dtype=np.int32)
+        evals_i = np.zeros(cap, dtype=np.uint32)
+        ps = params.as_struct()
+        rc = self.lib.lpb200_fit_mudisp_items(
+            self.ctx, C.byref(model), C.byref(ps), C.byref(control), ll.ctypes.data_as(A.c_double_p),
+            conv.ctypes.data_as(A.c_int32_p), C.byref(ns), C.byref(nt), theta0.ctypes.data_as(A.c_double_p),
+            theta.ctypes.data_as(A.c_double_p), ll_i.ctypes.data_as(A.c_double_p), conv_i.ctypes.data_as(A.c_int32_p),
+            evals_i.ctypes.data_as(C.POINTER(C.c_uint32)))
+        self._check(rc, allow=(A.E_NONFINITE,))
+        params.sync_back()
+        n_items, n = G * ns.value, nt.value
+        flat0, flat1 = theta0.ravel()[: n_items * n].reshape(n_items, n), theta.ravel()[: n_items * n].reshape(n_items, n)
+        return dict(ll=ll, conv=conv, rc=rc, n_starts=ns.value, theta0=flat0.copy(), theta=flat1.copy(),
+                    ll_items=ll_i[:n_items].copy(), conv_items=conv_i[:n_items].copy(), evals_items=evals_i[:n_items].copy())
+
     def fit_pi(self, model, params, control=None):
         control = control or A.default_control()
         n = self.n_cells if model.drop_fit_group == A.DROPFIT_PERCELL else 1
@@ -238,6 +264,14 @@ class Engine:
                                               len(a), int(use_library), q.ctypes.data_as(A.c_double_p),
                                               r.ctypes.data_as(A.c_double_p)))
         return q, r
+
+    def rcp64h_probe(self, hi, lo=0):
+        """MUFU.RCP64H of the doubles (hi[k], lo): (result hi words, result lo words)."""
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        oh, ol = np.zeros(len(hi), dtype=np.int32), np.zeros(len(hi), dtype=np.int32)
+        self._check(self.lib.lpb200_rcp64h_probe(self.ctx, hi.ctypes.data_as(A.c_int32_p), len(hi), int(lo),
+                                                 oh.ctypes.data_as(A.c_int32_p), ol.ctypes.data_as(A.c_int32_p)))
+        return oh, ol
 
 
 def lrt(ll_full, ll_red, ddf, library_path=None):

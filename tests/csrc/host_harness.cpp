@@ -106,6 +106,10 @@ extern "C" int hh_rosenbrock(int maxit, double reltol, double *par, double *valu
 extern "C" double hh_ll_obs(double x, double mu, double phi, double pi) {
     double logphi = log(phi);
     if (x == 0) return pi >= 0 ? lp_ll_zero_zinb(mu, phi, pi) : lp_ll_zero_nb(mu, phi, logphi);
+    if (lp_nb_small_x(x, phi)) {   // as lp_cell_ll: dnbinom_mu's x < 1e-10 * size branch
+        double v = (pi >= 0 ? log(1.0 - pi) : 0.0) + lp_dnbinom_small_x(x, mu, phi);
+        return v < LP_LL_FLOOR ? LP_LL_FLOOR : v;
+    }
     return lp_ll_nonzero(x, lp_nb_xphi_part(x, phi), mu, phi, pi >= 0 ? log(1.0 - pi) : 0.0);
 }
 

@@ -93,6 +93,14 @@ def main():
         total += zinb_obs(int(xs[j]), mu * mp.mpf(sf[j]), phi, float(pi))
     json.dump({"t": t.tolist(), "sf": sf.tolist(), "par": par, "phi": phi, "theta": theta.tolist(),
                "x": [int(v) for v in xs], "loglik": float(total)}, open(os.path.join(HERE, "tiny_gene.json"), "w"))
+    # 6. dnbinom beyond the 1e10 dispersion clamp (products with dispersion batch factors, spline dispersions):
+    #    R's dnbinom_mu takes its x < 1e-10 * size branch here
+    huge = []
+    for size in (1.5e10, 1e11, 1e12, 1e15, 1e20):
+        for mu in (1e-3, 0.7, 35.0, 4e3, 1e6):
+            for x in (1.0, 2.0, 9.0, 140.0, 60000.0):
+                huge.append({"x": x, "size": size, "mu": mu, "value": float(nb_logpmf(x, size, mu))})
+    json.dump(huge, open(os.path.join(HERE, "dnbinom_huge_size.json"), "w"), indent=0)
 
 
 if __name__ == "__main__":

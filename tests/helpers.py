@@ -75,3 +75,34 @@ def random_params(oracle, X, d, m, seed=5):
             for k in range(1, p.mat_drop.shape[1]):
                 p.mat_drop[:, k] = rng.normal(0, 0.3, N)
     return p
+
+
+def theta0_items(oracle, X, d, m, p0):
+    """Start vectors of the fit kernel's work items as lpb200_fit_mudisp builds them (fitMeanDispersion.R:349-364,
+    :621-663): theta = [log disp | log disp batch factors | mu coordinates | log mu batch factors], impulse fits
+    with 3 starts per gene in the order Peak, Valley, Prior.  Returns (theta0 [G * n_starts, n], n_starts)."""
+    G = d.n_genes
+    disp_cols = p0.mat_disp if m.disp_model == A.DISP_SPLINES else np.log(p0.mat_disp)
+    bdisp = [np.log(b[:, 1:]) for b in p0.batch_disp]
+    bmu = [np.log(b[:, 1:]) for b in p0.batch_mu]
+    if m.mu_model == A.MU_IMPULSE:
+        peak, valley = oracle.impulse_starts(X, d)
+        prior = p0.mat_mu.copy()
+        prior[:, 2:5] = np.log(prior[:, 2:5])
+        mus = [peak, valley, prior]
+    elif m.mu_model == A.MU_SPLINES:
+        mus = [p0.mat_mu]
+    else:
+        mus = [np.log(p0.mat_mu)]
+    rows = []
+    for i in range(G):
+        for mu in mus:
+            rows.append(np.concatenate([disp_cols[i]] + [b[i] for b in bdisp] + [mu[i]] + [b[i] for b in bmu]))
+    return np.ascontiguousarray(rows, dtype=np.float64), len(mus)
+
+
+def best_start(ll_items, n_starts):
+    """Per gene: index and value of the first maximum over its starts (fitMeanDispersion.R:664-671)."""
+    ll = np.asarray(ll_items).reshape(-1, n_starts)
+    best = np.argmax(ll, axis=1)   # first maximum
+    return best, ll[np.arange(len(ll)), best]

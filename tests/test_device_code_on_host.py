@@ -48,6 +48,24 @@ def test_device_obs_math_vs_mpmath_and_oracle(hh, oracle):
         assert abs(v - o) <= 1e-13 * max(1.0, abs(o)), r
 
 
+def test_dnbinom_beyond_the_dispersion_clamp(hh, oracle):
+    """phi > 1e10 (dispersion batch factors, spline dispersions): R's dnbinom_mu switches to its
+    x < 1e-10 * size formula; the device code and the oracle follow (R/srcLineagePulse_evalLogLik.R:136-140)."""
+    n_branch = 0
+    for r in golden("dnbinom_huge_size.json"):
+        v = hh.hh_ll_obs(r["x"], r["mu"], r["size"], -1.0)
+        o = oracle.dnbinom_mu_log(r["x"], r["size"], r["mu"])
+        want = max(r["value"], -700.0)
+        small_x = r["x"] < 1e-10 * r["size"]
+        n_branch += small_x
+        # the small-x formula drops O(mu x / size) terms (2e-9 at size 1.5e10); the dbinom_raw branch keeps R's
+        # size * 1e-17 digit loss
+        tol = 5e-9 if small_x else 1e-5
+        assert abs(max(o, -700.0) - want) <= tol * max(1.0, abs(want)), r
+        assert abs(v - max(o, -700.0)) <= 1e-13 * max(1.0, abs(o)), r
+    assert n_branch >= 60
+
+
 def _fit_gene(hh, d, m, X, i, th0, drop, pi_fixed, use_oracle_obs):
     hh.hh_use_oracle_obs(int(use_oracle_obs))
     out = np.zeros(len(th0))
