@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "lp_kernels.cuh"
+#include "lp_comm.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -40,11 +41,19 @@ struct lpb200_ctx {
     bool have_starts = false;
     std::vector<double> h_peak, h_valley;  // G x 7 column-major
     std::vector<double> h_bs_mu;           // host copy of the mu spline basis (for Pinv)
-    // collective
+    // collective: the gene shards of one matrix.  Either an NCCL communicator owned by the library
+    // (lpb200_comm_init: one process per GPU; lpb200_create_multi: one process, one shard context per device)
+    // or the host's all-reduce callback (lpb200_set_collective).
     int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
     lpb200_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
     double *d_xchg = nullptr;  // small exchange buffer
+    uint64_t allreduce_calls = 0, allreduce_bytes = 0;
+    // multi-device context (lpb200_create_multi): this object only dispatches to its shard contexts
+    std::vector<lpb200_ctx *> shards;
+    std::vector<int> bounds;       // gene range of shard k: [bounds[k], bounds[k + 1])
+    bool owns_stream = false;
     // stats
     lpb200_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -73,6 +82,30 @@ static FitKernelFn fit_kernel(bool u16, int variant, bool cl) {
     return cl ? fit_kernel_ct<int32_t, true>(variant) : fit_kernel_ct<int32_t, false>(variant);
 }
 static size_t fit_smem_bytes(bool cl) { return cl ? sizeof(FitSharedT<true>) : sizeof(FitSharedT<false>); }
+
+// multi-device contexts (lp_multi.cuh, included at the end of this file)
+static bool is_multi(const lpb200_ctx *c);
+static int multi_load_counts_dense(lpb200_ctx *ctx, int G, int N, const double *x);
+static int multi_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32_t *p, const int32_t *i, const double *x);
+static int multi_load_counts_i32(lpb200_ctx *ctx, int G, int N, const int32_t *x, int is_device);
+static int multi_set_design(lpb200_ctx *ctx, const lpb200_design *d);
+static int multi_row_means(lpb200_ctx *ctx, double *means);
+static int multi_init_params(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *out, double min_rowmean_global);
+static int multi_eval_loglik(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, double *ll);
+static int multi_impulse_starts(lpb200_ctx *ctx, double *peak, double *valley);
+static int multi_fit_mudisp_items(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll,
+                                  int32_t *conv, int32_t *n_starts, int32_t *n_theta, double *theta0, double *theta,
+                                  double *ll_items, int32_t *conv_items, uint32_t *evals_items);
+static int multi_fit_pi(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll, int32_t *conv);
+static int multi_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop, const lpb200_control *c,
+                           double min_rowmean_global, double *em_ll, int32_t *n_iter, int32_t *converged, double *ll_init,
+                           double *ll, int32_t *conv);
+static int multi_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_model *models, lpb200_params *params,
+                                 const lpb200_control *c, double min_rowmean_global, double *ll_init, double *em_ll,
+                                 int32_t *converged, double *ll, int32_t *conv, uint64_t *ole);
+static int multi_expand_fits(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids, int n_ids,
+                             int what, double *z);
+static int multi_get_stats(lpb200_ctx *ctx, lpb200_stats *s);
 
 static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -240,6 +273,11 @@ static void free_design(lpb200_ctx *c) {
 
 extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (!c) return;
+    if (is_multi(c)) {
+        for (lpb200_ctx *s : c->shards) lpb200_destroy(s);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     pool_release(c->device);
@@ -251,6 +289,8 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (c->d_nobs) cudaFree(c->d_nobs);
     if (c->d_xchg) cudaFree(c->d_xchg);
     for (cudaStream_t st : c->aux_streams) cudaStreamDestroy(st);
+    if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -260,12 +300,20 @@ extern "C" const char *lpb200_last_error(lpb200_ctx *c) { return c ? c->err.c_st
 
 extern "C" int lpb200_set_stream(lpb200_ctx *ctx, void *s) {
     if (!ctx) return LPB200_E_ARG;
+    if (is_multi(ctx)) return set_err(ctx, LPB200_E_ARG, "a multi-device context owns one stream per device");
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->owns_stream = false;
     ctx->stream = (cudaStream_t)s;
     return 0;
 }
 
 extern "C" int lpb200_set_collective(lpb200_ctx *ctx, int rank, int world, lpb200_allreduce_fn fn, void *user) {
+    if (is_multi(ctx)) return set_err(ctx, LPB200_E_ARG, "a multi-device context has its own communicator");
     if (!ctx || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return set_err(ctx, LPB200_E_ARG, "bad collective");
+    if (ctx->comm && nccl_api()) {
+        nccl_api()->CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
     ctx->rank = rank;
     ctx->world = world;
     ctx->allreduce = fn;
@@ -275,20 +323,91 @@ extern "C" int lpb200_set_collective(lpb200_ctx *ctx, int rank, int world, lpb20
 
 extern "C" int lpb200_get_stats(lpb200_ctx *ctx, lpb200_stats *s) {
     if (!ctx || !s) return LPB200_E_ARG;
+    if (is_multi(ctx)) return multi_get_stats(ctx, s);
     *s = ctx->stats;
     return 0;
 }
 extern "C" int lpb200_reset_stats(lpb200_ctx *ctx) {
     if (!ctx) return LPB200_E_ARG;
+    for (lpb200_ctx *c : ctx->shards) lpb200_reset_stats(c);
     ctx->stats = lpb200_stats{};
+    ctx->allreduce_calls = ctx->allreduce_bytes = 0;
+    return 0;
+}
+
+// ---- NCCL communicator of a one-process-per-GPU run -----------------------------------------------------------
+extern "C" int lpb200_comm_unique_id(char *id) {
+    NcclApi *nccl = nccl_api();
+    if (!nccl || !id) return LPB200_E_COMM;
+    ncclUniqueId u;
+    if (nccl->GetUniqueId(&u) != ncclSuccess) return LPB200_E_COMM;
+    memcpy(id, u.internal, LPB200_UNIQUE_ID_BYTES);
+    return 0;
+}
+
+extern "C" int lpb200_comm_init(lpb200_ctx *ctx, int rank, int world, const char *id) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) return set_err(ctx, LPB200_E_ARG, "a multi-device context has its own communicator");
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !id)) return set_err(ctx, LPB200_E_ARG, "comm_init: bad arguments");
+    NcclApi *nccl = nccl_api();
+    if (ctx->comm && nccl) {
+        nccl->CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->allreduce = nullptr;
+    if (world == 1) return 0;
+    if (!nccl) return set_err(ctx, LPB200_E_COMM, "NCCL library not found (set LPB200_NCCL_LIBRARY)");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, LPB200_UNIQUE_ID_BYTES);
+    ncclResult_t r = nccl->CommInitRank(&ctx->comm, world, u, rank);
+    if (r != ncclSuccess) {
+        ctx->comm = nullptr;
+        ctx->world = 1;
+        ctx->rank = 0;
+        return set_err(ctx, LPB200_E_COMM, "ncclCommInitRank failed: %s", nccl->GetErrorString(r));
+    }
+    return 0;
+}
+
+extern "C" int lpb200_comm_stats(lpb200_ctx *ctx, uint64_t *calls, uint64_t *bytes) {
+    if (!ctx || !calls || !bytes) return LPB200_E_ARG;
+    const lpb200_ctx *c = is_multi(ctx) ? ctx->shards[0] : ctx;
+    *calls = c->allreduce_calls;
+    *bytes = c->allreduce_bytes;
     return 0;
 }
 
 static int do_allreduce(lpb200_ctx *ctx, void *dev, size_t count, int dtype) {
     if (ctx->world <= 1) return 0;
+    ctx->allreduce_calls++;
+    ctx->allreduce_bytes += 8 * (uint64_t)count;
+    if (ctx->comm) {   // stream-ordered, in place
+        ncclResult_t r = nccl_api()->AllReduce(dev, dev, count, dtype == LPB200_I64 ? ncclInt64 : ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+        if (r != ncclSuccess) return set_err(ctx, LPB200_E_COMM, "ncclAllReduce failed: %s", nccl_api()->GetErrorString(r));
+        return 0;
+    }
     int rc = ctx->allreduce(ctx->allreduce_user, dev, count, dtype, (void *)ctx->stream);
     if (rc != 0) return set_err(ctx, LPB200_E_COMM, "all-reduce callback failed (%d)", rc);
     return 0;
+}
+
+// A failure on one shard (optim's non-finite error on a local gene, fitMeanDispersion.R:384-389) must reach every
+// shard before any of them returns: the others would otherwise wait in the next collective forever.  The
+// reference aborts the whole run on this error; so do all shards, together.
+static int sync_error(lpb200_ctx *ctx, int rc) {
+    if (ctx->world <= 1) return rc;
+    double v = rc != 0 ? 1.0 : 0.0;
+    if (cudaMemcpyAsync(ctx->d_xchg + 8, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return rc ? rc : LPB200_E_CUDA;
+    int rc2 = do_allreduce(ctx, ctx->d_xchg + 8, 1, LPB200_F64);
+    if (rc2) return rc ? rc : rc2;
+    if (cudaMemcpyAsync(&v, ctx->d_xchg + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return rc ? rc : LPB200_E_CUDA;
+    if (rc == 0 && v > 0) return set_err(ctx, LPB200_E_NONFINITE, "another gene shard reported an error (non-finite objective); the run is aborted on every shard");
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -358,7 +477,8 @@ static int finish_counts(lpb200_ctx *ctx, TmpCounts &tmp, int G, int N, size_t p
 
 static size_t row_pitch(int N) { return ((size_t)N + 63) / 64 * 64; }
 
-extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const double *x) {
+// rows [0, G) of an R matrix with leading dimension ld >= G (a gene shard of a larger matrix when ld > G)
+static int load_counts_dense_ld(lpb200_ctx *ctx, int G, int N, const double *x, size_t ld) {
     if (!ctx) return LPB200_E_CUDA;
     if (G <= 0 || N <= 0 || !x) return set_err(ctx, LPB200_E_ARG, "load_counts_dense: bad arguments");
     CK(cudaSetDevice(ctx->device));
@@ -373,7 +493,11 @@ extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const dou
     CK(d_slab.alloc(slab_cols * G));
     for (size_t j0 = 0; j0 < (size_t)N; j0 += slab_cols) {
         size_t nj = std::min(slab_cols, (size_t)N - j0);
-        CK(cudaMemcpyAsync(d_slab.p, x + j0 * G, sizeof(double) * nj * G, cudaMemcpyHostToDevice, ctx->stream));
+        if (ld == (size_t)G)
+            CK(cudaMemcpyAsync(d_slab.p, x + j0 * G, sizeof(double) * nj * G, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            CK(cudaMemcpy2DAsync(d_slab.p, sizeof(double) * G, x + j0 * ld, sizeof(double) * ld, sizeof(double) * G, nj,
+                                 cudaMemcpyHostToDevice, ctx->stream));
         dim3 grid((G + 31) / 32, (unsigned)((nj + 31) / 32)), block(32, 8);
         pack_dense_kernel<<<grid, block, 0, ctx->stream>>>(d_slab.p, G, (int)j0, (int)nj, d_i32, pitch);
         CK(cudaGetLastError());
@@ -382,8 +506,14 @@ extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const dou
     return finish_counts(ctx, tmp, G, N, pitch);
 }
 
+extern "C" int lpb200_load_counts_dense(lpb200_ctx *ctx, int G, int N, const double *x) {
+    if (is_multi(ctx)) return multi_load_counts_dense(ctx, G, N, x);
+    return load_counts_dense_ld(ctx, G, N, x, (size_t)std::max(G, 0));
+}
+
 extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32_t *p, const int32_t *i, const double *x) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) return multi_load_counts_csc(ctx, G, N, p, i, x);
     if (G <= 0 || N <= 0 || !p) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: bad arguments");
     if (p[0] != 0 || p[N] < 0 || (p[N] > 0 && (!i || !x))) return set_err(ctx, LPB200_E_ARG, "load_counts_csc: bad column pointers");
     for (int j = 0; j < N; j++)
@@ -415,6 +545,7 @@ extern "C" int lpb200_load_counts_csc(lpb200_ctx *ctx, int G, int N, const int32
 
 extern "C" int lpb200_load_counts_i32(lpb200_ctx *ctx, int G, int N, const int32_t *x, int is_device) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) return multi_load_counts_i32(ctx, G, N, x, is_device);
     if (G <= 0 || N <= 0 || !x) return set_err(ctx, LPB200_E_ARG, "load_counts_i32: bad arguments");
     CK(cudaSetDevice(ctx->device));
     size_t pitch = row_pitch(N);
@@ -429,6 +560,7 @@ extern "C" int lpb200_load_counts_i32(lpb200_ctx *ctx, int G, int N, const int32
 
 extern "C" int lpb200_row_means(lpb200_ctx *ctx, double *means) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) return multi_row_means(ctx, means);
     if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "counts not loaded");
     memcpy(means, ctx->row_means.data(), sizeof(double) * ctx->G);
     return 0;
@@ -470,6 +602,7 @@ static int upload(lpb200_ctx *ctx, const T *h, size_t n, const T **d_out) {
 
 extern "C" int lpb200_set_design(lpb200_ctx *ctx, const lpb200_design *d) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) return multi_set_design(ctx, d);
     if (!d) return set_err(ctx, LPB200_E_ARG, "design is NULL");
     if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "load counts before the design");
     if (d->n_genes != ctx->G || d->n_cells != ctx->N)
@@ -732,6 +865,7 @@ static int eval_loglik_impl(lpb200_ctx *ctx, const DevModel &M, const lpb200_par
 }
 
 extern "C" int lpb200_eval_loglik(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, double *ll) {
+    if (is_multi(ctx)) return multi_eval_loglik(ctx, m, p, ll);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -778,6 +912,7 @@ static int ensure_starts(lpb200_ctx *ctx) {
 }
 
 extern "C" int lpb200_impulse_starts(lpb200_ctx *ctx, double *peak, double *valley) {
+    if (is_multi(ctx)) return multi_impulse_starts(ctx, peak, valley);
     int rc = require_ready(ctx);
     if (rc) return rc;
     if ((rc = ensure_starts(ctx))) return rc;
@@ -1023,6 +1158,7 @@ static int fit_mudisp_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *p,
 
 extern "C" int lpb200_fit_mudisp(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll,
                                  int32_t *conv) {
+    if (is_multi(ctx)) return multi_fit_mudisp_items(ctx, m, p, c, ll, conv, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1036,6 +1172,7 @@ extern "C" int lpb200_fit_mudisp(lpb200_ctx *ctx, const lpb200_model *m, lpb200_
 extern "C" int lpb200_fit_mudisp_items(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c,
                                        double *ll, int32_t *conv, int32_t *n_starts, int32_t *n_theta, double *theta0,
                                        double *theta, double *ll_items, int32_t *conv_items, uint32_t *evals_items) {
+    if (is_multi(ctx)) return multi_fit_mudisp_items(ctx, m, p, c, ll, conv, n_starts, n_theta, theta0, theta, ll_items, conv_items, evals_items);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1231,6 +1368,7 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
 
 extern "C" int lpb200_fit_pi(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll,
                              int32_t *conv) {
+    if (is_multi(ctx)) return multi_fit_pi(ctx, m, p, c, ll, conv);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1316,6 +1454,7 @@ static int init_params_impl(lpb200_ctx *ctx, const DevModel &M, lpb200_params *o
 }
 
 extern "C" int lpb200_init_params(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *out, double min_rowmean_global) {
+    if (is_multi(ctx)) return multi_init_params(ctx, m, out, min_rowmean_global);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1348,6 +1487,7 @@ static int sum_ll(lpb200_ctx *ctx, const double *ll, int G, double *out) {
 extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop,
                                 const lpb200_control *c, double min_rowmean_global, double *em_ll, int32_t *n_iter,
                                 int32_t *converged, double *ll_init, double *ll, int32_t *conv) {
+    if (is_multi(ctx)) return multi_fit_model(ctx, m, p, fit_drop, c, min_rowmean_global, em_ll, n_iter, converged, ll_init, ll, conv);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1371,7 +1511,7 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
     int any_nonconv = 0;
     while (iter == 1 || (ll_new > ll_old * c->prec_em && iter <= max_cycles)) {  // :242-243
         if (fit_drop && (rc = fit_pi_impl(ctx, M, m->drop_fit_group, p, c, pill.data(), piconv.data()))) return rc;
-        if ((rc = fit_mudisp_impl(ctx, M, p, c, ll, conv))) return rc;
+        if ((rc = sync_error(ctx, fit_mudisp_impl(ctx, M, p, c, ll, conv)))) return rc;
         ll_old = ll_new;
         if ((rc = sum_ll(ctx, ll, G, &ll_new))) return rc;
         em_ll[iter - 1] = ll_new;
@@ -1400,6 +1540,7 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
 extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_model *models, lpb200_params *params,
                                       const lpb200_control *c, double min_rowmean_global, double *ll_init, double *em_ll,
                                       int32_t *converged, double *ll, int32_t *conv, uint64_t *ole) {
+    if (is_multi(ctx)) return multi_fit_model_multi(ctx, n_jobs, models, params, c, min_rowmean_global, ll_init, em_ll, converged, ll, conv, ole);
     int rc = require_ready(ctx);
     if (rc) return rc;
     enum { MAX_JOBS = 4 };
@@ -1459,7 +1600,7 @@ extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_
         if (ole) ole[j] = jobs[j].ole;
     }
     ctx->stats.kernel_ms += span;
-    if (first_err) return first_err;
+    if ((first_err = sync_error(ctx, first_err))) return first_err;
     for (int j = 0; j < n_jobs; j++) {
         double ll_new;
         if ((rc = sum_ll(ctx, jobs[j].ll, G, &ll_new))) return rc;
@@ -1485,6 +1626,7 @@ extern "C" int lpb200_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_
 // ---------------------------------------------------------------------------------------------
 extern "C" int lpb200_expand_fits(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids,
                                   int n_ids, int what, double *z) {
+    if (is_multi(ctx)) return multi_expand_fits(ctx, m, p, gene_ids, n_ids, what, z);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1597,6 +1739,7 @@ extern "C" int lpb200_lrt(const double *ll_full, const double *ll_red, int ddf, 
 // ---------------------------------------------------------------------------------------------
 extern "C" int lpb200_fp64_peak(lpb200_ctx *ctx, double *tflops) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) ctx = ctx->shards[0];
     CK(cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 16;
     DevBuf<double> out;
@@ -1621,6 +1764,7 @@ extern "C" int lpb200_fp64_peak(lpb200_ctx *ctx, double *tflops) {
 
 extern "C" int lpb200_libm_probe(lpb200_ctx *ctx, const double *x, int n, int use_library, double *exp_out, double *log_out) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) ctx = ctx->shards[0];
     if (!x || !exp_out || !log_out || n <= 0) return set_err(ctx, LPB200_E_ARG, "libm_probe: bad arguments");
     CK(cudaSetDevice(ctx->device));
     DevBuf<double> dx, de, dl;
@@ -1640,6 +1784,7 @@ extern "C" int lpb200_libm_probe(lpb200_ctx *ctx, const double *x, int n, int us
 extern "C" int lpb200_div_probe(lpb200_ctx *ctx, const double *a, const double *b, int n, int use_library, double *quot_out,
                                 double *rcp_out) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) ctx = ctx->shards[0];
     if (!a || !b || !quot_out || !rcp_out || n <= 0) return set_err(ctx, LPB200_E_ARG, "div_probe: bad arguments");
     CK(cudaSetDevice(ctx->device));
     DevBuf<double> da, db, dq, dr;
@@ -1660,6 +1805,7 @@ extern "C" int lpb200_div_probe(lpb200_ctx *ctx, const double *a, const double *
 
 extern "C" int lpb200_rcp64h_probe(lpb200_ctx *ctx, const int32_t *hi, int n, int32_t lo, int32_t *out_hi, int32_t *out_lo) {
     if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) ctx = ctx->shards[0];
     if (!hi || !out_hi || !out_lo || n <= 0) return set_err(ctx, LPB200_E_ARG, "rcp64h_probe: bad arguments");
     CK(cudaSetDevice(ctx->device));
     DevBuf<int32_t> dh, doh, dol;
@@ -1675,3 +1821,5 @@ extern "C" int lpb200_rcp64h_probe(lpb200_ctx *ctx, const int32_t *hi, int n, in
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+#include "lp_multi.cuh"

@@ -250,17 +250,21 @@ __device__ void lp_eval_points(const FitArgs &A, SH &S, const CT *row, int gene,
         for (int o = 16; o >= npad; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane < npad && lane < nk) S.red[buf][v][lane] = acc;
     }
-    if (CL) lp_cluster_sync();
-    else __syncthreads();
-    if (tid < nk) {   // the 64 virtual warps in index order; virtual warp v lives in CTA (v mod P) / nwarps
-        double s = 0.0;
-        if (CL) {
-#pragma unroll 8
-            for (int v = 0; v < LP_VW; v++) s += lp_dsmem_load(&S.red[buf][v][tid], (unsigned)((v % P) / nwarps));
-        } else {
-#pragma unroll 8
-            for (int v = 0; v < LP_VW; v++) s += S.red[0][v][tid];
+    if (CL) {
+        // every CTA collects the partial sums of the virtual warps its neighbours ran: one distributed-shared-memory
+        // load per thread and value, all in flight together (a serial walk over 64 remote values costs ~7 us)
+        lp_cluster_sync();
+        for (int e = tid; e < LP_VW * nk; e += blockDim.x) {
+            const int v = e / nk, kk = e - v * nk;
+            const unsigned owner = (unsigned)((v % P) / nwarps);
+            if (owner != crank) S.red[buf][v][kk] = lp_dsmem_load(&S.red[buf][v][kk], owner);
         }
+    }
+    __syncthreads();
+    if (tid < nk) {   // the 64 virtual warps in index order
+        double s = 0.0;
+#pragma unroll 8
+        for (int v = 0; v < LP_VW; v++) s += S.red[buf][v][tid];
         out_vals[tid] = s;
     }
     if (tid == 0) S.epoch++;
