@@ -274,6 +274,12 @@ def declare_product_prototypes(lib):
         "lpb200_n_batch_cols": (C.c_int, [c_int32_p, C.c_int]),
         "lpb200_deg_freedom": (C.c_int, [P(Model), P(Design)]),
         "lpb200_create": (vp, [C.c_int]),
+        "lpb200_create_multi": (vp, [c_int32_p, C.c_int]),
+        "lpb200_n_shards": (C.c_int, [vp]),
+        "lpb200_shard_bounds": (C.c_int, [vp, c_int32_p]),
+        "lpb200_comm_unique_id": (C.c_int, [C.c_char_p]),
+        "lpb200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
+        "lpb200_comm_stats": (C.c_int, [vp, P(C.c_uint64), P(C.c_uint64)]),
         "lpb200_destroy": (None, [vp]),
         "lpb200_last_error": (C.c_char_p, [vp]),
         "lpb200_set_stream": (C.c_int, [vp, vp]),
@@ -315,8 +321,30 @@ class LibraryMissing(RuntimeError):
     pass
 
 
+UNIQUE_ID_BYTES = 128
+
+
+def _point_at_bundled_nccl():
+    """The library binds NCCL with dlopen (lp_comm.cuh).  Inside a Python environment that ships NCCL as a wheel
+    (nvidia-nccl-cu12, which torch uses) point it at that copy, so that this process never holds two different
+    NCCL builds under one SONAME."""
+    if os.environ.get("LPB200_NCCL_LIBRARY"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["LPB200_NCCL_LIBRARY"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load_library(path: str | None = None):
     """dlopen the CUDA library.  There is no CPU fallback: a missing library is an error."""
+    _point_at_bundled_nccl()
     path = path or os.environ.get("LPB200_LIBRARY") or default_library_path()
     if not os.path.exists(path):
         raise LibraryMissing(

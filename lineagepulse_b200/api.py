@@ -51,7 +51,7 @@ class CountMatrix:
     on first use and stays resident for every later fit on this object.
     """
 
-    def __init__(self, data, rownames=None, colnames=None, device=0):
+    def __init__(self, data, rownames=None, colnames=None, device=0, devices=None):
         import scipy.sparse as sp
         self.sparse = sp.issparse(data)
         self.data = data.tocsc() if self.sparse else np.asarray(data)
@@ -60,11 +60,12 @@ class CountMatrix:
         self.rownames = np.asarray(rownames if rownames is not None else [f"Gene_{i + 1}" for i in range(G)])
         self.colnames = np.asarray(colnames if colnames is not None else [f"cell_{j + 1}" for j in range(N)])
         self.device = device
+        self.devices = None if devices is None else [int(v) for v in devices]   # several GPUs: genes are dealt to them
         self._engine = None
 
     def engine(self) -> Engine:
         if self._engine is None:
-            e = Engine(self.device)
+            e = Engine(self.device, devices=self.devices)
             G, N = self.shape
             if self.sparse:
                 m = self.data
@@ -84,7 +85,7 @@ class CountMatrix:
 
     def subset_genes(self, idx):
         d = self.data[idx, :] if not self.sparse else self.data.tocsr()[idx, :].tocsc()
-        return CountMatrix(d, self.rownames[idx], self.colnames, self.device)
+        return CountMatrix(d, self.rownames[idx], self.colnames, self.device, self.devices)
 
 
 def _as_counts(matCounts) -> CountMatrix:
@@ -463,7 +464,7 @@ def _fit_result(lsMu, lsDisp, lsDrop, r, ncyc, dt, boolVerbose):
 def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersMu=None, matPiConstPredictors=None,
                   vecNormConstExternal=None, strDispModelFull="constant", strDispModelRed="constant",
                   strMuModel="splines", scaDFSplinesDisp=3, scaDFSplinesMu=6, scaMaxEstimationCycles=20,
-                  boolVerbose=True, boolSuperVerbose=False, rownames=None, colnames=None, device=0):
+                  boolVerbose=True, boolSuperVerbose=False, rownames=None, colnames=None, device=0, devices=None):
     """processSCData.R:85-365: input checks, cell / gene filtering, object construction."""
     import scipy.sparse as sp
     if isinstance(counts, str):
@@ -569,7 +570,7 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
     if boolVerbose:
         message(strReport.rstrip("\n"))
     objLP = LineagePulseObject(
-        dfAnnotationProc=dfProc, matCountsProc=CountMatrix(m, rownames[gene_idx], colnames[cell_idx], device),
+        dfAnnotationProc=dfProc, matCountsProc=CountMatrix(m, rownames[gene_idx], colnames[cell_idx], device, devices),
         scaDFSplinesDisp=scaDFSplinesDisp, scaDFSplinesMu=scaDFSplinesMu, strReport=strReport,
         vecAllGenes=rownames, vecConfoundersMu=vecConfoundersMu, vecConfoundersDisp=vecConfoundersDisp)
     return {"objLP": objLP,
@@ -706,16 +707,19 @@ def runLineagePulse(counts, dfAnnotation=None, vecConfoundersMu=None, vecConfoun
                     strDispModelFull="constant", strDispModelRed="constant", strDropModel="logistic",
                     strDropFitGroup="PerCell", scaDFSplinesMu=6, scaDFSplinesDisp=3, matPiConstPredictors=None,
                     vecNormConstExternal=None, boolEstimateNoiseBasedOnH0=True, scaMaxEstimationCycles=20,
-                    scaNProc=1, boolVerbose=True, boolSuperVerbose=False, rownames=None, colnames=None, device=0):
-    """main_LineagePulse.R:219-323.  ``scaNProc`` stays in the signature; the BiocParallel fork
-    pool it sized (main_LineagePulse.R:271-275) is replaced by the GPU."""
+                    scaNProc=1, boolVerbose=True, boolSuperVerbose=False, rownames=None, colnames=None, device=0,
+                    devices=None):
+    """main_LineagePulse.R:219-323.  ``scaNProc`` stays in the signature; the BiocParallel fork pool it sized
+    (main_LineagePulse.R:271-275) is replaced by the GPUs: ``device`` names one, ``devices=[0, 1, ...]`` several
+    (one gene-sharded context, lpb200_create_multi; results are bit-identical to the one-GPU run)."""
     ls = processSCData(counts=counts, dfAnnotation=dfAnnotation, vecConfoundersMu=vecConfoundersMu,
                        vecConfoundersDisp=vecConfoundersDisp, matPiConstPredictors=matPiConstPredictors,
                        vecNormConstExternal=vecNormConstExternal, strMuModel=strMuModel,
                        strDispModelFull=strDispModelFull, strDispModelRed=strDispModelRed,
                        scaDFSplinesMu=scaDFSplinesMu, scaDFSplinesDisp=scaDFSplinesDisp,
                        scaMaxEstimationCycles=scaMaxEstimationCycles, boolVerbose=boolVerbose,
-                       boolSuperVerbose=boolSuperVerbose, rownames=rownames, colnames=colnames, device=device)
+                       boolSuperVerbose=boolSuperVerbose, rownames=rownames, colnames=colnames, device=device,
+                       devices=devices)
     objLP = ls["objLP"]
 
     def log(msg):

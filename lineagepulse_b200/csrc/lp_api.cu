@@ -46,6 +46,7 @@ struct lpb200_ctx {
     // or the host's all-reduce callback (lpb200_set_collective).
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    Loopback *loopback = nullptr;   // shards of a multi-device context that share one device (testing)
     lpb200_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
     double *d_xchg = nullptr;  // small exchange buffer
@@ -274,7 +275,12 @@ static void free_design(lpb200_ctx *c) {
 extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (!c) return;
     if (is_multi(c)) {
+        Loopback *L = c->shards[0]->loopback;
         for (lpb200_ctx *s : c->shards) lpb200_destroy(s);
+        if (L) {
+            for (void *t : L->tmp) if (t) cudaFree(t);
+            delete L;
+        }
         delete c;
         return;
     }
@@ -387,6 +393,11 @@ static int do_allreduce(lpb200_ctx *ctx, void *dev, size_t count, int dtype) {
     if (ctx->comm) {   // stream-ordered, in place
         ncclResult_t r = nccl_api()->AllReduce(dev, dev, count, dtype == LPB200_I64 ? ncclInt64 : ncclFloat64, ncclSum, ctx->comm, ctx->stream);
         if (r != ncclSuccess) return set_err(ctx, LPB200_E_COMM, "ncclAllReduce failed: %s", nccl_api()->GetErrorString(r));
+        return 0;
+    }
+    if (ctx->loopback) {
+        int rc = loopback_allreduce(ctx->loopback, ctx->rank, dev, count, dtype == LPB200_F64, ctx->stream);
+        if (rc != 0) return set_err(ctx, LPB200_E_COMM, "loopback all-reduce failed (%d)", rc);
         return 0;
     }
     int rc = ctx->allreduce(ctx->allreduce_user, dev, count, dtype, (void *)ctx->stream);

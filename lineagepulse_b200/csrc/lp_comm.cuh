@@ -51,13 +51,67 @@ static NcclApi *nccl_api() {
     });
     return api.handle ? &api : nullptr;
 }
-static const char *nccl_load_error() {
-    static NcclApi *dummy = nccl_api();
-    (void)dummy;
-    static std::string msg;
-    NcclApi *a = nccl_api();
-    if (a) return "";
-    // the static inside nccl_api() keeps the dlerror text
-    msg = "NCCL library not found (set LPB200_NCCL_LIBRARY)";
-    return msg.c_str();
+
+// Loopback communicator: several shard contexts on ONE device (lpb200_create_multi with a repeated device id).
+// NCCL cannot put two ranks on one GPU; here the shards' host threads meet at a barrier and every shard adds up
+// all the shards' buffers (same device, same address space) in rank order.  Exists so that the multi-device
+// machinery -- slicing, gathering, the collective sequence of the EM loop -- runs and is tested on a single-GPU
+// box exactly as it does over NCCL; there is no reason to use it in production.
+#include <condition_variable>
+struct Loopback {
+    int n = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long generation = 0;
+    std::vector<const void *> bufs;
+    std::vector<void *> tmp;
+    std::vector<size_t> tmp_words;
+    bool broken = false;
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long gen = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            generation++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != gen || broken; });
+        }
+    }
+};
+
+__global__ void loopback_sum_kernel(const void *b0, const void *b1, const void *b2, const void *b3, const void *b4, const void *b5,
+                                    const void *b6, const void *b7, int n, void *out, size_t count, int is_f64) {
+    const void *b[8] = {b0, b1, b2, b3, b4, b5, b6, b7};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        if (is_f64) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += reinterpret_cast<const double *>(b[k])[i];
+            reinterpret_cast<double *>(out)[i] = s;
+        } else {
+            long long s = 0;
+            for (int k = 0; k < n; k++) s += reinterpret_cast<const long long *>(b[k])[i];
+            reinterpret_cast<long long *>(out)[i] = s;
+        }
+    }
+}
+
+static int loopback_allreduce(Loopback *L, int rank, void *dev, size_t count, int is_f64, cudaStream_t stream) {
+    if (L->n > 8) return 1;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 2;
+    L->bufs[rank] = dev;
+    if (L->tmp_words[rank] < count) {
+        if (L->tmp[rank]) cudaFree(L->tmp[rank]);
+        if (cudaMalloc(&L->tmp[rank], 8 * count) != cudaSuccess) return 3;
+        L->tmp_words[rank] = count;
+    }
+    L->barrier();   // every shard's buffer is complete and registered
+    const void *b[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < L->n; k++) b[k] = L->bufs[k];
+    loopback_sum_kernel<<<64, 256, 0, stream>>>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], L->n, L->tmp[rank], count, is_f64);
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 4;
+    L->barrier();   // every shard has read every buffer
+    if (cudaMemcpyAsync(dev, L->tmp[rank], 8 * count, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return 5;
+    return 0;
 }

@@ -24,13 +24,18 @@ static std::vector<int> shard_bounds(int G, int n) {
 }
 
 extern "C" lpb200_ctx *lpb200_create_multi(const int *devices, int n) {
-    if (!devices || n < 1) return nullptr;
+    if (!devices || n < 1 || n > 64) return nullptr;
     if (n == 1) return lpb200_create(devices[0]);
-    for (int a = 0; a < n; a++)
+    bool repeated = false, all_same = true;
+    for (int a = 0; a < n; a++) {
+        if (devices[a] != devices[0]) all_same = false;
         for (int b = a + 1; b < n; b++)
-            if (devices[a] == devices[b]) return nullptr;
-    NcclApi *nccl = nccl_api();
-    if (!nccl) return nullptr;
+            if (devices[a] == devices[b]) repeated = true;
+    }
+    // distinct devices: NCCL.  One device n times (n <= 8): the loopback communicator (lp_comm.cuh; testing).
+    if (repeated && (!all_same || n > 8)) return nullptr;
+    NcclApi *nccl = repeated ? nullptr : nccl_api();
+    if (!repeated && !nccl) return nullptr;
     lpb200_ctx *parent = new lpb200_ctx();
     parent->device = devices[0];
     std::vector<ncclComm_t> comms(n, nullptr);
@@ -42,15 +47,24 @@ extern "C" lpb200_ctx *lpb200_create_multi(const int *devices, int n) {
         if (cudaSetDevice(devices[k]) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
         else c->owns_stream = true;
     }
-    if (ok && nccl->CommInitAll(comms.data(), n, devices) != ncclSuccess) ok = false;
+    if (ok && nccl && nccl->CommInitAll(comms.data(), n, devices) != ncclSuccess) ok = false;
     if (!ok) {
         for (ncclComm_t cm : comms) if (cm) nccl->CommDestroy(cm);
         for (lpb200_ctx *c : parent->shards) lpb200_destroy(c);
         delete parent;
         return nullptr;
     }
+    Loopback *L = nullptr;
+    if (repeated) {
+        L = new Loopback();
+        L->n = n;
+        L->bufs.assign(n, nullptr);
+        L->tmp.assign(n, nullptr);
+        L->tmp_words.assign(n, 0);
+    }
     for (int k = 0; k < n; k++) {
         parent->shards[k]->comm = comms[k];
+        parent->shards[k]->loopback = L;
         parent->shards[k]->rank = k;
         parent->shards[k]->world = n;
     }

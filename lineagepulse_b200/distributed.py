@@ -34,14 +34,45 @@ class _CudaWordView:
                                          "data": (ptr, False), "version": 3, "strides": None}
 
 
+def init_comm(engine, group=None):
+    """One process per GPU (torchrun): give ``engine`` the library's own NCCL communicator.  Rank 0 creates the
+    NCCL unique id, torch.distributed only carries its 128 bytes to the other ranks; every later cross-shard sum
+    is an ncclAllReduce issued by the library on its own stream (no Python in the loop)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    engine.init_comm(rank, world, box[0])
+    return rank, world
+
+
 def make_allreduce(group=None):
-    """all-reduce(sum) callback for Engine.set_collective on CUDA buffers."""
+    """all-reduce(sum) callback for Engine.set_collective on CUDA buffers (the host-callback alternative to
+    ``init_comm``, e.g. for a transport other than NCCL).  The collective is enqueued on the stream the library
+    names, on the device the buffer lives on."""
     import torch
     import torch.distributed as dist
 
     def allreduce(ptr: int, count: int, dtype: int, stream: int):
-        t = torch.as_tensor(_CudaWordView(ptr, count, dtype), device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        dev = torch.cuda.current_device()
+        try:   # the buffer's own device, not torch's current one
+            from cuda import cudart  # cuda-python
+            err, attr = cudart.cudaPointerGetAttributes(ptr)
+            if int(err) == 0:
+                dev = int(attr.device)
+        except Exception:
+            pass
+        with torch.cuda.device(dev):
+            t = torch.as_tensor(_CudaWordView(ptr, count, dtype), device=torch.device("cuda", dev))
+            assert t.data_ptr() == ptr, "the all-reduce buffer was copied instead of wrapped"
+            if stream:
+                ext = torch.cuda.ExternalStream(stream, device=dev)
+                with torch.cuda.stream(ext):
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            else:   # legacy default stream: order explicitly
+                torch.cuda.synchronize(dev)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                torch.cuda.synchronize(dev)
 
     return allreduce
 

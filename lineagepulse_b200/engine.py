@@ -20,14 +20,29 @@ class LPB200Error(RuntimeError):
 
 
 class Engine:
-    def __init__(self, device: int = 0, library_path: str | None = None):
+    """``Engine(device)``: one GPU.  ``Engine(devices=[0, 1, ...])``: one context over several GPUs of this
+    process (lpb200_create_multi): same methods, whole-matrix arguments and results, genes dealt to the devices,
+    NCCL inside the library -- the replacement of the reference's ``scaNProc`` worker pool."""
+
+    def __init__(self, device: int = 0, library_path: str | None = None, devices=None):
         self.lib = A.load_library(library_path)
         if self.lib.lpb200_abi_version() != 1:
             raise RuntimeError("liblpb200.so ABI version mismatch")
-        self.ctx = self.lib.lpb200_create(int(device))
-        if not self.ctx:
-            raise LPB200Error(A.E_CUDA, f"cannot open CUDA device {device} (no GPU / driver?) -- "
-                                         "this library has no CPU fallback")
+        if devices is not None and len(devices) > 1:
+            devs = np.ascontiguousarray(devices, dtype=np.int32)
+            self.devices = [int(v) for v in devs]
+            self.ctx = self.lib.lpb200_create_multi(devs.ctypes.data_as(A.c_int32_p), len(devs))
+            if not self.ctx:
+                raise LPB200Error(A.E_CUDA, f"cannot open CUDA devices {self.devices} as one context (no GPU / driver, "
+                                             "or NCCL not found: set LPB200_NCCL_LIBRARY) -- this library has no CPU fallback")
+        else:
+            if devices is not None and len(devices) == 1:
+                device = devices[0]
+            self.devices = [int(device)]
+            self.ctx = self.lib.lpb200_create(int(device))
+            if not self.ctx:
+                raise LPB200Error(A.E_CUDA, f"cannot open CUDA device {device} (no GPU / driver?) -- "
+                                             "this library has no CPU fallback")
         self.design: A.DesignData | None = None
         self._cb = None
         self.n_genes = self.n_cells = 0
@@ -67,6 +82,31 @@ class Engine:
                 return 1
         self._cb = A.ALLREDUCE_FN(_cb) if world > 1 else A.ALLREDUCE_FN()
         self._check(self.lib.lpb200_set_collective(self.ctx, rank, world, self._cb, None))
+
+    def init_comm(self, rank: int, world: int, unique_id: bytes | None):
+        """One process per GPU: join the library's own NCCL communicator (lpb200_comm_init).  ``unique_id`` are the
+        bytes of ``Engine.comm_unique_id()`` created on rank 0 and distributed by the host (see
+        ``lineagepulse_b200.distributed.init_comm``)."""
+        self._check(self.lib.lpb200_comm_init(self.ctx, int(rank), int(world), unique_id))
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(A.UNIQUE_ID_BYTES)
+        rc = self.lib.lpb200_comm_unique_id(buf)
+        if rc != 0:
+            raise LPB200Error(rc, "NCCL library not found (set LPB200_NCCL_LIBRARY)")
+        return buf.raw
+
+    def comm_stats(self):
+        """(all-reduce calls, payload bytes) since the last reset_stats()."""
+        calls, nbytes = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.lpb200_comm_stats(self.ctx, C.byref(calls), C.byref(nbytes)))
+        return int(calls.value), int(nbytes.value)
+
+    def shard_bounds(self):
+        n = self.lib.lpb200_n_shards(self.ctx)
+        b = np.zeros(n + 1, dtype=np.int32)
+        self._check(self.lib.lpb200_shard_bounds(self.ctx, b.ctypes.data_as(A.c_int32_p)))
+        return [int(v) for v in b]
 
     # -- data ------------------------------------------------------------------------------
     def load_counts_dense(self, x):

@@ -101,3 +101,76 @@ def simulateContinuousDataSet(scaNCells, scaNConst, scaNLin, scaNImp, scaMumax=1
     genes = np.array([f"gene_{i + 1}" for i in range(G)])
     return {"annot": {"cell": cells, "continuous": hid["pt"]}, "counts": counts, "genes": genes,
             "hidden": {"disp": disp, **hid}}
+
+
+# ---------------------------------------------------------------------------------------------
+# Benchmark workloads generated ON THE DEVICE, any gene range at a time (bench.py: the strong-scaling
+# 20 000 x 100 000 matrix is 2e9 draws -- minutes of numpy and 8 GB of host memory per rank otherwise).
+# Same recipe as simulateContinuousDataSet (+ group / batch effects for the C4 shape); the
+# draws of genes [16 c, 16 c + 16) come from a generator seeded with (seed, c), so any sharding that starts on
+# multiples of 16 genes sees the same matrix.
+# ---------------------------------------------------------------------------------------------
+def workload_recipe(n_genes, seed, mumax=100.0, sd_amp=3.0, dropout=0.1, n_groups=0, n_batches=0):
+    """Per-gene hidden parameters (host, O(G)): 50 % constant / 25 % linear / 25 % impulse trajectories in a fixed
+    random gene order (contiguous gene shards then carry the same mix), dispersions 3 + N(0, 0.5); with
+    ``n_groups``: half the genes get group means m exp(N(0, 0.5)); with ``n_batches``: batch factors exp(N(0, 0.3))."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_const, n_lin = n_genes // 2, n_genes // 4
+    n_imp = n_genes - n_const - n_lin
+    hid = simulate_hidden_means(rng, 2, n_const, n_lin, n_imp, mumax, sd_amp)
+    kind = np.r_[np.zeros(n_const, np.int8), np.ones(n_lin, np.int8), np.full(n_imp, 2, np.int8)]
+    par = np.zeros((n_genes, 6))
+    par[:n_const, 0] = hid["mu_const"]
+    par[n_const:n_const + n_lin, 0] = hid["lin_start"]
+    par[n_const:n_const + n_lin, 1] = hid["lin_end"]
+    for k, nm in enumerate(("beta", "t1", "t2", "h0", "h1", "h2")):
+        par[n_const + n_lin:, k] = hid[nm]
+    disp = np.maximum(3 + rng.normal(0.0, 0.5, size=n_genes), 0.05)
+    order = rng.permutation(n_genes)
+    rec = {"n_genes": n_genes, "seed": int(seed), "kind": kind[order], "par": par[order], "disp": disp[order],
+           "dropout": float(dropout), "group_fac": None, "batch_fac": None}
+    if n_groups:
+        gf = np.ones((n_genes, n_groups))
+        affected = rng.uniform(size=n_genes) < 0.5
+        gf[affected] = np.exp(rng.normal(0.0, 0.5, size=(int(affected.sum()), n_groups)))
+        rec["group_fac"] = gf
+    if n_batches:
+        bf = np.exp(rng.normal(0.0, 0.3, size=(n_genes, n_batches)))
+        bf[:, 0] = 1.0
+        rec["batch_fac"] = bf
+    return rec
+
+
+def simulate_rows_device(rec, n_cells, lo, hi, device, group_idx=None, batch_idx=None, dtype=None):
+    """Rows [lo, hi) of the workload's count matrix as an int32 torch tensor on ``device`` (lo a multiple of 16)."""
+    import torch
+    assert lo % 16 == 0
+    dev = torch.device(device)
+    pt = torch.arange(n_cells, dtype=torch.float64, device=dev) / max(n_cells - 1, 1)
+    out = torch.empty((hi - lo, n_cells), dtype=dtype or torch.int32, device=dev)
+    gidx = None if group_idx is None else torch.as_tensor(np.asarray(group_idx), dtype=torch.long, device=dev)
+    bidx = None if batch_idx is None else torch.as_tensor(np.asarray(batch_idx), dtype=torch.long, device=dev)
+    gen = torch.Generator(device=dev)
+    for c0 in range(lo, hi, 16):
+        c1 = min(hi, c0 + 16)
+        kind = torch.as_tensor(rec["kind"][c0:c1].astype(np.int64), device=dev)[:, None]
+        par = torch.as_tensor(rec["par"][c0:c1], dtype=torch.float64, device=dev)
+        a, b, c, d, e, f = (par[:, k:k + 1] for k in range(6))
+        const = a.expand(-1, n_cells)
+        lin = a + pt[None, :] * (b - a)
+        # impulse (simulateDataSet.R:85-88): par = beta, t1, t2, h0, h1, h2; guarded for the non-impulse rows
+        h1 = torch.where(kind == 2, e, torch.ones_like(e))
+        imp = (1.0 / h1) * (d + (h1 - d) / (1.0 + torch.exp(-a * (pt[None, :] - b)))) * (f + (h1 - f) / (1.0 + torch.exp(a * (pt[None, :] - c))))
+        mu = torch.where(kind == 0, const, torch.where(kind == 1, lin, imp))
+        if rec["group_fac"] is not None and gidx is not None:
+            mu = mu * torch.as_tensor(rec["group_fac"][c0:c1], dtype=torch.float64, device=dev)[:, gidx]
+        if rec["batch_fac"] is not None and bidx is not None:
+            mu = mu * torch.as_tensor(rec["batch_fac"][c0:c1], dtype=torch.float64, device=dev)[:, bidx]
+        mu = torch.clamp(mu, min=SCA_MIN_MU)
+        phi = torch.as_tensor(rec["disp"][c0:c1], dtype=torch.float64, device=dev)[:, None]
+        gen.manual_seed(rec["seed"] * 1000003 + c0 // 16)
+        lam = torch._standard_gamma(phi.expand(-1, n_cells).contiguous(), generator=gen) * (mu / phi)   # rnbinom(mu, size)
+        x = torch.poisson(lam, generator=gen)
+        keep = torch.rand(x.shape, generator=gen, device=dev, dtype=torch.float64) >= rec["dropout"]
+        out[c0 - lo:c1 - lo] = (x * keep).to(out.dtype)
+    return out

@@ -38,6 +38,8 @@ def test_no_cpu_fallback():
     with pytest.raises(lp.LPB200Error):
         lp.Engine(0)
     with pytest.raises(lp.LPB200Error):
+        lp.Engine(devices=[0, 1])       # lpb200_create_multi: NULL without devices
+    with pytest.raises(lp.LPB200Error):
         lp.evalLogLikMatrix(np.ones((3, 4), dtype=np.int32), {"lsMuModelGlobal": {"strMuModel": "constant", "vecNormConst": np.ones(4)}, "matMuModel": np.ones((3, 1))},
                             {"lsDispModelGlobal": {"strDispModel": "constant"}, "matDispModel": np.ones((3, 1))},
                             {"lsDropModelGlobal": {"strDropModel": "none"}})
