@@ -75,9 +75,20 @@ static FitKernelFn fit_kernel_ct(int variant) {
     case 2: return fit_mudisp_kernel<CT, LP_MU_FAST_CONST, true, CL>;
     case 3: return fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, false, CL>;
     case 4: return fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, true, CL>;
-    default: return fit_mudisp_kernel<CT, -1, false, CL>;
+    default: break;
     }
+    if (!CL) {   // the covariate-model kernels are built for one CTA per item only
+        switch (variant) {
+        case 5: return fit_mudisp_kernel<CT, LP_MU_FAST_GROUPS, false, false>;
+        case 6: return fit_mudisp_kernel<CT, LP_MU_FAST_GROUPS, true, false>;
+        case 7: return fit_mudisp_kernel<CT, LP_MU_FAST_SPLINES, false, false>;
+        case 8: return fit_mudisp_kernel<CT, LP_MU_FAST_SPLINES, true, false>;
+        default: break;
+        }
+    }
+    return fit_mudisp_kernel<CT, -1, false, CL>;
 }
+#define LP_N_FIT_VARIANTS 9
 static FitKernelFn fit_kernel(bool u16, int variant, bool cl) {
     if (u16) return cl ? fit_kernel_ct<uint16_t, true>(variant) : fit_kernel_ct<uint16_t, false>(variant);
     return cl ? fit_kernel_ct<int32_t, true>(variant) : fit_kernel_ct<int32_t, false>(variant);
@@ -246,7 +257,7 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
     // wait for running kernels, which would serialise the concurrent fits of lpb200_fit_model_multi
     for (int ct = 0; ct < 2; ct++)
         for (int cl = 0; cl < 2; cl++)
-            for (int v = 0; v < 5; v++) {
+            for (int v = 0; v < LP_N_FIT_VARIANTS; v++) {
                 cudaFuncSetAttribute((const void *)fit_kernel(ct != 0, v, cl != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)fit_smem_bytes(cl != 0));
                 cudaFuncAttributes fa;
@@ -1005,23 +1016,37 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     CK(cudaMemcpyAsync(J.d_theta0.p, J.theta0.data(), sizeof(double) * J.theta0.size(), cudaMemcpyHostToDevice, J.stream));
     CK(cudaMemsetAsync(J.d_queue.p, 0, sizeof(int), J.stream));
     const int threads = fit_threads(N);
-    // CTAs per work item: long rows are evaluated by a thread-block cluster, which divides the duration of an item
-    // -- and with it the item-length tail of the dynamic queue -- by the cluster size; the result does not depend
-    // on it (virtual-warp summation order, lp_kernels.cuh).  Short rows stay with one CTA per item: the cluster
-    // barrier per evaluation (~0.2 us) would show against a 20-40 us pass.
+    // CTAs per work item.  A thread-block cluster working on one item divides the duration of an item -- and with it
+    // the item-length tail of the dynamic queue -- by the cluster size; the result does not depend on it
+    // (virtual-warp summation order, lp_kernels.cuh).  Measured (profiles/README.md): it pays when a launch has few
+    // items per CTA slot (592 genes x 100 000 cells: -9 % with 2 CTAs per item); with 25 items per slot the
+    // concurrent B / C / D launches already back-fill each other's tails and 4 CTAs per item cost 10 % (fewer
+    // co-resident clusters, redundant state machines).  Short rows stay with one CTA per item: the cluster barrier
+    // per evaluation would show against a 20-40 us pass.
     int cluster = ctx->cluster;
-    if (cluster == 0) cluster = (N >= 65536) ? 4 : (N >= 32768 ? 2 : 1);
+    if (cluster == 0) {
+        const size_t slots = (size_t)ctx->sm_count * ctx->ctas_per_sm;
+        cluster = 1;
+        if (N >= 32768 && J.n_items < 8 * slots) cluster = 2;
+        if (N >= 65536 && J.n_items < 3 * slots) cluster = 4;
+    }
     if (threads != LP_FIT_THREADS) cluster = 1;
     const bool cl = cluster > 1;
     const size_t smem = fit_smem_bytes(cl);
     // persistent CTAs: as many as stay resident (64 registers per thread; shared memory allows 3 per SM)
     const int smem_limit = (int)((227 * 1024) / (smem + 1024));
     const int per_sm = std::max(1, std::min(ctx->ctas_per_sm * (LP_FIT_THREADS / threads), smem_limit));
-    // specialised kernels for the hot configurations, generic kernel otherwise
-    const bool fast = !ctx->no_fastpath && lp_disp_is_scalar(D, M) && D.n_conf_mu == 0 &&
-                      (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE) &&
-                      (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
-    const int variant = !fast ? 0 : (M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) + (M.drop_model == LPB200_DROP_LOGISTIC ? 1 : 0);
+    // specialised kernels for the hot configurations (scalar dispersion, drop-out "none" / fixed "logistic": constant or
+    // impulse mean without confounders -- C1-C3; groups or splines mean with mean batch factors -- C4 / C5), generic otherwise
+    const bool fast_base = !ctx->no_fastpath && lp_disp_is_scalar(D, M) &&
+                           (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
+    const bool fast_ci = fast_base && D.n_conf_mu == 0 && (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE);
+    const bool fast_cov = fast_base && !fast_ci && (M.mu_model == LPB200_MU_GROUPS || M.mu_model == LPB200_MU_SPLINES);
+    if (fast_cov) cluster = 1;
+    const bool fast = fast_ci || fast_cov;
+    const int zinb_bit = (M.drop_model == LPB200_DROP_LOGISTIC) ? 1 : 0;
+    const int variant = fast_ci ? (M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) + zinb_bit
+                                : (fast_cov ? (M.mu_model == LPB200_MU_GROUPS ? 5 : 7) + zinb_bit : 0);
     FitKernelFn kernel = fit_kernel(ctx->is_u16, variant, cl);
     CK(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * per_sm);

@@ -164,6 +164,56 @@ struct FastLane {
         return lp_fast_cell<MU, ZINB>(F, x, j, tt, sf, pi_ptr, l1m_ptr, tabp, tab_len);
     }
 };
+// Group means or a spline mean model, mean batch factors, one scalar dispersion per gene, drop-out "none" or
+// gene-wise fixed (BASELINE configs C4 / C5).  The point stays in shared memory (its group means / spline
+// coefficients / batch factors are indexed by the cell); what the specialisation buys is the pruned code -- the
+// operations are lp_cell_ll's, in lp_cell_ll's order, so the bits are the generic evaluator's.
+template <typename CT, int MUK, bool ZINB>
+struct CovariateLane {
+    const DevDesign *D;
+    const PointNat *P;
+    const double *tabp, *pi_ptr, *l1m_ptr;
+    const CT *row;
+    double phi, logphi;
+    int tab_len, nnz;
+    template <typename SH>
+    __device__ __forceinline__ void setup(const FitArgs &A, SH &S, const CT *row_, int gene, int k, int tab_len_,
+                                          const double *pi_ptr_, const double *l1m_ptr_) {
+        D = &A.D;
+        P = &S.pts[k];
+        phi = P->disp[0];
+        logphi = lp_log(phi);
+        tab_len = tab_len_;
+        tabp = tab_len > 0 ? S.tab[S.tab_of_point[k]] : nullptr;
+        pi_ptr = pi_ptr_;
+        l1m_ptr = l1m_ptr_;
+        row = row_;
+        nnz = A.C.nnz[gene];
+    }
+    __device__ __forceinline__ double term(int r, int j) const {
+        const int x = (r < nnz) ? lp_load_count(row, j) : 0;
+        const int N = D->N;
+        double mu;
+        if (MUK == LPB200_MU_GROUPS) {
+            mu = P->mu[D->group[j]];
+        } else {
+            double lin = 0.0;
+            for (int k = 0; k < D->k_mu; k++) lin += D->bs_mu[j + (size_t)k * N] * P->mu[k];
+            mu = lp_exp(lin);
+        }
+        int o = 0;
+        for (int c = 0; c < D->n_conf_mu; c++) {
+            mu = mu * P->bmu[o + D->bidx_mu[(size_t)c * N + j]];
+            o += D->nb_mu[c];
+        }
+        const double mus = mu * (D->sf ? D->sf[j] : 1.0);
+        if (x == 0) return ZINB ? lp_ll_zero_zinb(mus, phi, pi_ptr[j]) : lp_ll_zero_nb(mus, phi, logphi);
+        const double xd = (double)x;
+        const double xphi = (x < tab_len) ? tabp[x] : lp_nb_xphi_part_cold(xd, phi);
+        return lp_ll_nonzero(xd, xphi, mus, phi, ZINB ? l1m_ptr[j] : 0.0);
+    }
+};
+
 template <typename CT>
 struct GenericLane {
     const FitArgs *A;
@@ -350,8 +400,12 @@ fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
                 }
                 __syncthreads();
                 const int ntabs = lp_request_ntabs(req, base);
-                if constexpr (MU >= 0)
+                if constexpr (MU == LP_MU_FAST_CONST || MU == LP_MU_FAST_IMPULSE)
                     lp_eval_points<CL, FastLane<CT, MU, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
+                else if constexpr (MU == LP_MU_FAST_GROUPS)
+                    lp_eval_points<CL, CovariateLane<CT, LPB200_MU_GROUPS, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
+                else if constexpr (MU == LP_MU_FAST_SPLINES)
+                    lp_eval_points<CL, CovariateLane<CT, LPB200_MU_SPLINES, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
                 else
                     lp_eval_points<CL, GenericLane<CT>>(A, S, row, gene, xmax, kc, ntabs, scalar_phi, S.vals + base, pi_ptr, l1m_ptr);
             }

@@ -1,5 +1,6 @@
-/* Minimal stand-in for R's Rinternals.h: declares ONLY what r_shim/lp_rshim.c uses, so that the shim's
- * signatures can be compile-checked in an image without R.  Not a functional R. */
+/* Minimal stand-in for R's Rinternals.h: declares ONLY what r_shim/lp_rshim.c uses (plus the constructors the
+ * test driver needs), so that the shim can be compiled -- and, linked with tests/csrc/fake_r_runtime.c, RUN --
+ * in an image without R. */
 #ifndef FAKE_RINTERNALS_H
 #define FAKE_RINTERNALS_H
 #include <stddef.h>
@@ -24,6 +25,9 @@ int *INTEGER(SEXP);
 int asInteger(SEXP);
 int asLogical(SEXP);
 SEXP allocVector(unsigned int, long);
+SEXP mkChar(const char *);
+SEXP setAttrib(SEXP, SEXP, SEXP);
+void SET_STRING_ELT(SEXP, int, SEXP);
 SEXP PROTECT(SEXP);
 void UNPROTECT(int);
 char *R_alloc(size_t, int);

@@ -6,9 +6,11 @@
  * (fitMeanDispersion.R:853-859, fitDropout.R:418-422, evalLogLik.R:307-313, fitModel.R:137-158),
  * calls the C ABI of include/lpb200.h and re-packs the results under the reference's names.
  *
- * STATUS: R is not installed in the build image, so this file is compile-checked against
- * r_shim/fake_R/Rinternals.h (a minimal stand-in declaring only the API used here) by
- * tests/test_host_logic.py::test_r_shim_compiles; it has NOT been run against a real R.
+ * STATUS: R is not installed in the build image.  This file is compiled against r_shim/fake_R/Rinternals.h
+ * (a stand-in declaring only the R API used here) and, linked with the functional stand-in runtime
+ * tests/csrc/fake_r_runtime.c, it is RUN on the GPU by tests/test_gpu_parity.py::test_r_shim_runs_on_the_gpu
+ * (lp_create -> lp_load_counts_csc -> lp_set_design -> lp_fit_model -> lp_fit_models -> lp_eval_loglik -> lp_lrt,
+ * compared bit for bit with the ctypes path); it has NOT been run against a real R.
  * Build inside the package with:  PKG_LIBS = -L<dir> -llpb200   (src/Makevars)
  */
 #include <R.h>
@@ -44,9 +46,13 @@ static void check(lpb200_ctx *ctx, int rc) { /* any optimiser error aborts, as f
 }
 
 /* ---- context + data ------------------------------------------------------------------------- */
-/* .Call("lp_create", device) -> external pointer with finalizer */
-SEXP lp_create(SEXP device) {
-    lpb200_ctx *ctx = lpb200_create(asInteger(device));
+/* .Call("lp_create", devices) -> external pointer with finalizer.  devices: integer vector of CUDA device ids;
+ * one id = one GPU, several = one gene-sharded context over all of them (lpb200_create_multi): what scaNProc /
+ * MulticoreParam(workers = scaNProc) was for the CPU path (main_LineagePulse.R:271-275). */
+SEXP lp_create(SEXP devices) {
+    int n = LENGTH(devices);
+    if (n < 1) error("LineagePulse: lp_create needs at least one device id");
+    lpb200_ctx *ctx = (n == 1) ? lpb200_create(INTEGER(devices)[0]) : lpb200_create_multi(INTEGER(devices), n);
     if (!ctx) error("LineagePulse: no usable CUDA device (there is no CPU fallback)");
     SEXP ptr = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);

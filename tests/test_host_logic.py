@@ -150,14 +150,39 @@ def test_lrt_host_arithmetic_vs_mpmath_and_oracle(oracle):
     assert np.isnan(p[1]) and np.isnan(padj[1]) and not np.isnan(padj[0])
 
 
-def test_r_shim_compiles():
-    """R is absent from the image: the .Call shim is compile-checked (syntax + prototypes of the C ABI)
-    against r_shim/fake_R, a stand-in declaring only the R API it uses."""
+def _build_rshim_harness():
+    """r_shim/lp_rshim.c + the functional stand-in R runtime + the driver, linked against liblpb200.so."""
     import subprocess
-    subprocess.check_call(["gcc", "-std=gnu11", "-fsyntax-only", "-Werror=implicit-function-declaration",
-                           "-Werror=incompatible-pointer-types", "-I", os.path.join(ROOT, "r_shim", "fake_R"),
-                           os.path.join(ROOT, "r_shim", "lp_rshim.c")])
+    build = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(build, exist_ok=True)
+    out = os.path.join(build, "librshimharness.so")
+    srcs = [os.path.join(ROOT, "r_shim", "lp_rshim.c"), os.path.join(ROOT, "tests", "csrc", "fake_r_runtime.c"),
+            os.path.join(ROOT, "tests", "csrc", "rshim_driver.c")]
+    libdir = os.path.join(ROOT, "lineagepulse_b200")
+    deps = srcs + [os.path.join(ROOT, "include", "lpb200.h"), os.path.join(ROOT, "r_shim", "fake_R", "Rinternals.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
+        subprocess.check_call(["gcc", "-std=gnu11", "-O1", "-fPIC", "-shared", "-Werror=implicit-function-declaration",
+                               "-Werror=incompatible-pointer-types", "-I", os.path.join(ROOT, "r_shim", "fake_R")] + srcs +
+                              ["-o", out, "-Wl,-Bsymbolic", "-L", libdir, "-l:liblpb200.so", f"-Wl,-rpath,{libdir}", "-lm"])   # -Bsymbolic: error() is also a glibc symbol
+    return out
+
+
+def test_r_shim_compiles_and_links():
+    """R is absent from the image: the .Call shim is compiled against r_shim/fake_R (a stand-in declaring only the R
+    API it uses), linked with the functional stand-in runtime and liblpb200.so; without a GPU its lp_create must
+    raise an R error (no CPU fallback).  The GPU run is tests/test_gpu_parity.py::test_r_shim_runs_on_the_gpu."""
+    lib = C.CDLL(_build_rshim_harness())
     src = open(os.path.join(ROOT, "r_shim", "lp_rshim.c")).read()
     for sym in ("lpb200_fit_mudisp", "lpb200_fit_pi", "lpb200_eval_loglik", "lpb200_fit_model", "lpb200_lrt",
-                "lpb200_load_counts_csc", "lpb200_set_design"):
+                "lpb200_load_counts_csc", "lpb200_set_design", "lpb200_create_multi", "lpb200_fit_model_multi"):
         assert sym in src
+    wr = open(os.path.join(ROOT, "r_shim", "R", "lpb200_wrappers.R")).read()
+    for fn in ("lpAttachCounts <- function", "fitMuDisp <- function", "fitPi <- function", "evalLogLikMatrix <- function",
+               "fitModel <- function", "fitLPModels <- function", "fitModelsConcurrently <- function"):
+        assert fn in wr
+    assert wr.count("(") == wr.count(")") and wr.count("{") == wr.count("}")   # R cannot parse it here; at least balanced
+    import torch
+    if not torch.cuda.is_available():
+        err = C.create_string_buffer(512)
+        assert lib.rs_released_context_raises(err) == 1
+        assert b"no usable CUDA device" in err.value
