@@ -46,6 +46,8 @@ struct lpb200_ctx {
     // or the host's all-reduce callback (lpb200_set_collective).
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    bool comm_borrowed = false;     // the communicator belongs to the process-wide cache (lp_multi.cuh)
+    struct CommSet *comm_set = nullptr;
     Loopback *loopback = nullptr;   // shards of a multi-device context that share one device (testing)
     lpb200_allreduce_fn allreduce = nullptr;
     void *allreduce_user = nullptr;
@@ -118,6 +120,7 @@ static int multi_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_model
 static int multi_expand_fits(lpb200_ctx *ctx, const lpb200_model *m, const lpb200_params *p, const int32_t *gene_ids, int n_ids,
                              int what, double *z);
 static int multi_get_stats(lpb200_ctx *ctx, lpb200_stats *s);
+static void release_comms(struct CommSet *cs);
 
 static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -288,6 +291,7 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (is_multi(c)) {
         Loopback *L = c->shards[0]->loopback;
         for (lpb200_ctx *s : c->shards) lpb200_destroy(s);
+        release_comms(c->comm_set);
         if (L) {
             for (void *t : L->tmp) if (t) cudaFree(t);
             delete L;
@@ -306,7 +310,7 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (c->d_nobs) cudaFree(c->d_nobs);
     if (c->d_xchg) cudaFree(c->d_xchg);
     for (cudaStream_t st : c->aux_streams) cudaStreamDestroy(st);
-    if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    if (c->comm && !c->comm_borrowed && nccl_api()) nccl_api()->CommDestroy(c->comm);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1236,6 +1240,68 @@ static void launch_pi_eval(lpb200_ctx *ctx, const PiArgs &A) {
     pi_eval_kernel<CT><<<grid, 128, 0, ctx->stream>>>(A);
 }
 
+// Tail of the lock-step loop on a SHARDED run.  A cell that needs thousands of BFGS iterations would cost one
+// all-reduce round trip per objective evaluation; instead the few remaining cells' count columns, the gene
+// parameters and the gene-wise drop-out predictors of every shard are gathered once on every shard (a summing
+// all-reduce of buffers in which each shard fills only its own gene range -- any transport that can all-reduce
+// can do it), and every shard finishes all remaining cells with pi_tail_kernel over the full gene range.  The
+// 16-gene summation blocks and their exact integer combination are those of the lock-step path, so the states
+// stay identical on every shard and equal to a single-device run, bit for bit.
+static int fit_pi_sharded_tail(lpb200_ctx *ctx, const PiArgs &A, const double *d_nat, const int *d_list, int n_tail) {
+    const int G = ctx->G, world = ctx->world, n_nat = lp_n_nat(A.M), P = A.D.P;
+    int rc;
+    // gene ranges of the shards
+    std::vector<long long> gs(world, 0);
+    gs[ctx->rank] = G;
+    DevBuf<long long> d_gs;
+    CK(d_gs.alloc(world));
+    CK(cudaMemcpyAsync(d_gs.p, gs.data(), sizeof(long long) * world, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = do_allreduce(ctx, d_gs.p, world, LPB200_I64))) return rc;
+    CK(cudaMemcpyAsync(gs.data(), d_gs.p, sizeof(long long) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    long long g_off = 0, g_tot = 0;
+    for (int r = 0; r < world; r++) {
+        if (r < ctx->rank) g_off += gs[r];
+        g_tot += gs[r];
+    }
+    if (g_off % LP_PI_BLOCK != 0) return set_err(ctx, LPB200_E_ARG, "gene shards must start on multiples of %d genes", LP_PI_BLOCK);
+    // gene parameters of all shards
+    DevBuf<double> d_nat_all, d_pred_all;
+    CK(d_nat_all.alloc((size_t)g_tot * n_nat));
+    CK(cudaMemsetAsync(d_nat_all.p, 0, sizeof(double) * (size_t)g_tot * n_nat, ctx->stream));
+    CK(cudaMemcpyAsync(d_nat_all.p + (size_t)g_off * n_nat, d_nat, sizeof(double) * (size_t)G * n_nat, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = do_allreduce(ctx, d_nat_all.p, (size_t)g_tot * n_nat, LPB200_F64))) return rc;
+    if (P > 0) {   // matPiConstPredictors: G x P column-major on every shard -> g_tot x P
+        CK(d_pred_all.alloc((size_t)g_tot * P));
+        CK(cudaMemsetAsync(d_pred_all.p, 0, sizeof(double) * (size_t)g_tot * P, ctx->stream));
+        CK(cudaMemcpy2DAsync(d_pred_all.p + g_off, sizeof(double) * g_tot, A.D.pi_pred, sizeof(double) * G, sizeof(double) * G, P,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = do_allreduce(ctx, d_pred_all.p, (size_t)g_tot * P, LPB200_F64))) return rc;
+    }
+    // count columns of the remaining cells over all genes, cell-major (row length even: the buffer travels as int64 words)
+    const size_t ld = ((size_t)g_tot + 1) / 2 * 2;
+    DevBuf<int32_t> d_cols;
+    CK(d_cols.alloc((size_t)n_tail * ld));
+    CK(cudaMemsetAsync(d_cols.p, 0, sizeof(int32_t) * (size_t)n_tail * ld, ctx->stream));
+    dim3 grid((unsigned)std::min(64, (G + 255) / 256), (unsigned)n_tail);
+    if (ctx->is_u16) pi_gather_counts_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>(A.C, G, d_list, n_tail, (int)g_off, d_cols.p, ld);
+    else pi_gather_counts_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(A.C, G, d_list, n_tail, (int)g_off, d_cols.p, ld);
+    CK(cudaGetLastError());
+    if ((rc = do_allreduce(ctx, d_cols.p, (size_t)n_tail * ld / 2, LPB200_I64))) return rc;
+    PiArgs T = A;
+    T.D.G = (int)g_tot;
+    T.D.pi_pred = P > 0 ? d_pred_all.p : nullptr;
+    T.nat = d_nat_all.p;
+    T.tail_counts = d_cols.p;
+    T.tail_ld = ld;
+    if (ctx->is_u16) pi_tail_kernel<uint16_t><<<n_tail, 256, 0, ctx->stream>>>(T, d_list);
+    else pi_tail_kernel<int32_t><<<n_tail, 256, 0, ctx->stream>>>(T, d_list);
+    CK(cudaGetLastError());
+    ctx->stats.launches += 2;
+    CK(cudaStreamSynchronize(ctx->stream));   // the gathered buffers are released on return
+    return 0;
+}
+
 static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, lpb200_params *p, const lpb200_control *c,
                        double *ll, int32_t *conv) {
     const int G = ctx->G, N = ctx->N, q = M.q_drop;
@@ -1256,9 +1322,10 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     n_chunks = (G + gpc - 1) / gpc;
     CK(d_nat.alloc(nat.size()));
     CK(d_drop.alloc((size_t)N * q));
-    CK(d_partial.alloc((size_t)3 * n_chunks * LP_PI_KP * N));
-    CK(d_vals_i.alloc((size_t)3 * LP_PI_KP * N));
-    CK(d_vals.alloc((size_t)LP_PI_KP * N));
+    const int kp = std::max(1, 2 * q);   // live point columns of a round (a gradient's 2q central-difference points)
+    CK(d_partial.alloc((size_t)3 * n_chunks * kp * N));
+    CK(d_vals_i.alloc((size_t)3 * kp * N));
+    CK(d_vals.alloc((size_t)kp * N));
     CK(d_states.alloc(N));
     CK(d_active.alloc(1));
     CK(d_total.alloc(LP_PI_KP));
@@ -1273,6 +1340,9 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     A.partial_i = d_partial.p;
     A.vals_i = d_vals_i.p;
     A.vals = d_vals.p;
+    A.kp = kp;
+    A.tail_counts = nullptr;
+    A.tail_ld = 0;
     A.genes_per_chunk = gpc;
     A.n_chunks = n_chunks;
     A.shared_nk = 0;
@@ -1300,7 +1370,7 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
             CK(cudaGetLastError());
             pi_reduce_kernel<<<nb, 128, 0, ctx->stream>>>(A);
             CK(cudaGetLastError());
-            if ((rc = do_allreduce(ctx, d_vals_i.p, (size_t)3 * LP_PI_KP * N, LPB200_I64))) return rc;
+            if ((rc = do_allreduce(ctx, d_vals_i.p, (size_t)3 * kp * N, LPB200_I64))) return rc;   // the live columns only
             pi_combine_kernel<<<nb, 128, 0, ctx->stream>>>(A);
             CK(cudaGetLastError());
             pi_advance_kernel<<<nb, 128, 0, ctx->stream>>>(A);
@@ -1313,14 +1383,18 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
             CK(cudaStreamSynchronize(ctx->stream));
             if (active == 0) break;
             if (round >= 8) check_every = 4;
-            if (ctx->world == 1 && active <= tail_threshold) {
-                CK(cudaMemsetAsync(d_active.p, 0, sizeof(int), ctx->stream));
-                pi_compact_kernel<<<nb, 128, 0, ctx->stream>>>(A, d_list.p, d_active.p);
+            if (active <= tail_threshold) {
+                pi_compact_kernel<<<1, 256, 0, ctx->stream>>>(A, d_list.p, d_active.p);
                 CK(cudaGetLastError());
-                if (ctx->is_u16) pi_tail_kernel<uint16_t><<<active, 256, 0, ctx->stream>>>(A, d_list.p);
-                else pi_tail_kernel<int32_t><<<active, 256, 0, ctx->stream>>>(A, d_list.p);
-                CK(cudaGetLastError());
-                ctx->stats.launches += 2;
+                ctx->stats.launches++;
+                if (ctx->world == 1) {
+                    if (ctx->is_u16) pi_tail_kernel<uint16_t><<<active, 256, 0, ctx->stream>>>(A, d_list.p);
+                    else pi_tail_kernel<int32_t><<<active, 256, 0, ctx->stream>>>(A, d_list.p);
+                    CK(cudaGetLastError());
+                    ctx->stats.launches++;
+                } else if ((rc = fit_pi_sharded_tail(ctx, A, d_nat.p, d_list.p, active))) {
+                    return rc;
+                }
                 break;
             }
         }
@@ -1372,7 +1446,7 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
         CK(cudaGetLastError());
         pi_reduce_kernel<<<nb, 128, 0, ctx->stream>>>(A);
         CK(cudaGetLastError());
-        if ((rc = do_allreduce(ctx, d_vals_i.p, (size_t)3 * LP_PI_KP * N, LPB200_I64))) return rc;
+        if ((rc = do_allreduce(ctx, d_vals_i.p, (size_t)3 * kp * N, LPB200_I64))) return rc;
         pi_combine_kernel<<<nb, 128, 0, ctx->stream>>>(A);
         CK(cudaGetLastError());
         pi_total_kernel<<<nk, 256, 0, ctx->stream>>>(d_vals.p, N, d_total.p);   // every shard sums the same cells in the same order

@@ -611,9 +611,13 @@ struct PiArgs {
     CountView C;
     const double *nat;      // [G][n_nat] natural-scale gene parameters
     PiState *states;        // [N]
-    long long *partial_i;   // [3][n_chunks][LP_PI_KP][N]: exact (a, b, bad) sums of the chunk's 16-gene blocks
-    long long *vals_i;      // [3][LP_PI_KP][N]: exact (a, b, bad) sums over blocks -- the all-reduced block
-    double *vals;           // [LP_PI_KP][N]
+    int kp;                 // live point columns of a round: 2q (buffers below hold kp columns, not LP_PI_KP)
+    long long *partial_i;   // [3][n_chunks][kp][N]: exact (a, b, bad) sums of the chunk's 16-gene blocks
+    long long *vals_i;      // [3][kp][N]: exact (a, b, bad) sums over blocks -- the all-reduced block
+    double *vals;           // [kp][N]
+    // tail of a sharded run: the remaining cells' counts over ALL genes (gathered from every shard), cell-major
+    const int32_t *tail_counts;   // [n_tail][tail_ld] or nullptr (then the tail reads the resident matrix)
+    size_t tail_ld;
     int genes_per_chunk, n_chunks;
     int shared_nk;          // > 0: ForAllCells, every cell evaluates shared_theta[0..shared_nk)
     double shared_theta[LP_PI_KP * LP_PI_NP];  // optimiser coordinates
@@ -718,11 +722,11 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
         }
     }
     if (j < D.N) {
-        const size_t plane = (size_t)A.n_chunks * LP_PI_KP * D.N;
+        const size_t plane = (size_t)A.n_chunks * A.kp * D.N;
 #pragma unroll
         for (int k = 0; k < LP_PI_KP; k++) {
             if (k < nk) {
-                const size_t o = ((size_t)blockIdx.y * LP_PI_KP + k) * D.N + j;
+                const size_t o = ((size_t)blockIdx.y * A.kp + k) * D.N + j;
                 A.partial_i[o] = ex[k].a;
                 A.partial_i[plane + o] = ex[k].b;
                 A.partial_i[2 * plane + o] = ex[k].bad;
@@ -741,13 +745,13 @@ __global__ void pi_reduce_kernel(PiArgs A) {
         int req = A.states[j].req;
         nk = (req == LP_REQ_F) ? 1 : (req == LP_REQ_GRAD ? 2 * A.M.q_drop : 0);
     }
-    const size_t plane = (size_t)LP_PI_KP * A.D.N;
-    for (int k = 0; k < LP_PI_KP; k++) {
+    const size_t plane = (size_t)A.kp * A.D.N;
+    for (int k = 0; k < A.kp; k++) {
         ExactSum s = {0, 0, 0};
         if (k < nk) {
-            const size_t cplane = (size_t)A.n_chunks * LP_PI_KP * A.D.N;
+            const size_t cplane = (size_t)A.n_chunks * A.kp * A.D.N;
             for (int c = 0; c < A.n_chunks; c++) {
-                const size_t oc = ((size_t)c * LP_PI_KP + k) * A.D.N + j;
+                const size_t oc = ((size_t)c * A.kp + k) * A.D.N + j;
                 s.a += A.partial_i[oc];
                 s.b += A.partial_i[cplane + oc];
                 s.bad += A.partial_i[2 * cplane + oc];
@@ -764,8 +768,8 @@ __global__ void pi_reduce_kernel(PiArgs A) {
 __global__ void pi_combine_kernel(PiArgs A) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= A.D.N) return;
-    const size_t plane = (size_t)LP_PI_KP * A.D.N;
-    for (int k = 0; k < LP_PI_KP; k++) {
+    const size_t plane = (size_t)A.kp * A.D.N;
+    for (int k = 0; k < A.kp; k++) {
         const size_t o = (size_t)k * A.D.N + j;
         A.vals[o] = lp_exact_value(A.vals_i[o], A.vals_i[plane + o], A.vals_i[2 * plane + o]);
     }
@@ -787,7 +791,7 @@ __global__ void pi_advance_kernel(PiArgs A) {
     PiState &st = A.states[j];
     if (st.req == LP_REQ_NONE) return;
     double v[LP_PI_KP];
-    for (int k = 0; k < LP_PI_KP; k++) v[k] = A.vals[(size_t)k * A.D.N + j];
+    for (int k = 0; k < A.kp; k++) v[k] = A.vals[(size_t)k * A.D.N + j];
     bfgs_advance(st, v);
     if (st.req != LP_REQ_NONE) atomicAdd(A.n_active, 1);
 }
@@ -810,10 +814,28 @@ __global__ void pi_finish_kernel(PiArgs A, double *drop_out, double *ll, int *co
 // CTA each, which runs the remaining BFGS iterations inside the kernel (no launch / host round
 // trip per objective evaluation).  The CTA strides over the genes of its cell; reads of the
 // gene-major matrix are strided, which is irrelevant for a handful of cells.
-__global__ void pi_compact_kernel(PiArgs A, int *list, int *count) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= A.D.N) return;
-    if (A.states[j].req != LP_REQ_NONE) list[atomicAdd(count, 1)] = j;
+// the still-active cells in cell order (one CTA: the list must be the same on every shard of a sharded run)
+__global__ void __launch_bounds__(256) pi_compact_kernel(PiArgs A, int *list, int *count) {
+    __shared__ int warp_cnt[8];
+    __shared__ int run;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) run = 0;
+    __syncthreads();
+    for (int base = 0; base < A.D.N; base += 256) {
+        const int j = base + tid;
+        const bool act = j < A.D.N && A.states[j].req != LP_REQ_NONE;
+        const unsigned b = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) warp_cnt[warp] = __popc(b);
+        __syncthreads();
+        int off = run;
+        for (int w = 0; w < warp; w++) off += warp_cnt[w];
+        if (act) list[off + __popc(b & ((1u << lane) - 1u))] = j;
+        __syncthreads();
+        if (tid == 0)
+            for (int w = 0; w < 8; w++) run += warp_cnt[w];
+        __syncthreads();
+    }
+    if (tid == 0) *count = run;
 }
 
 template <typename CT>
@@ -830,6 +852,8 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
     PiState &st = A.states[j];
     const double s = D.sf ? D.sf[j] : 1.0;
     const CT *base = reinterpret_cast<const CT *>(A.C.ptr);
+    // sharded run: D.G, A.nat and D.pi_pred span ALL genes and the cell's counts come from the gathered buffer
+    const int32_t *gathered = A.tail_counts ? A.tail_counts + (size_t)blockIdx.x * A.tail_ld : nullptr;
     for (;;) {
         if (tid == 0) {
             int req = st.req;
@@ -864,7 +888,7 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
             for (int k = 0; k < LP_PI_KP; k++) acc[k] = 0.0;
             const int i1 = min(D.G, (blk + 1) * LP_PI_BLOCK);
             for (int i = blk * LP_PI_BLOCK; i < i1; i++) {
-                const int x = lp_load_count(base + (size_t)i * A.C.pitch, j);
+                const int x = gathered ? gathered[i] : lp_load_count(base + (size_t)i * A.C.pitch, j);
                 if (x < 0) continue;
                 PointNat P;
                 lp_nat_load(M, A.nat + (size_t)i * n_nat, P);
@@ -907,6 +931,18 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
         if (tid == 0) bfgs_advance(st, s_vals);
         __syncthreads();
     }
+}
+
+// sharded tail: this shard's counts of the remaining cells into the gathered cell-major buffer (columns
+// [g_off, g_off + G) of every cell's row; the other shards' columns stay zero for the summing all-reduce)
+template <typename CT>
+__global__ void pi_gather_counts_kernel(CountView C, int G, const int *list, int n_tail, int g_off, int32_t *out, size_t ld) {
+    const int k = blockIdx.y;
+    if (k >= n_tail) return;
+    const int j = list[k];
+    const CT *base = reinterpret_cast<const CT *>(C.ptr);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < G; i += gridDim.x * blockDim.x)
+        out[(size_t)k * ld + g_off + i] = lp_load_count(base + (size_t)i * C.pitch, j);
 }
 
 // ForAllCells: total[k] = sum_j vals[k][j]  (one CTA per point, fixed order)

@@ -9,9 +9,48 @@
 // of the EM log-likelihood.  This is the replacement of the reference's BiocParallel pool
 // (main_LineagePulse.R:271-275: MulticoreParam(workers = scaNProc)) that the public API reaches.
 #pragma once
+#include <chrono>
 #include <thread>
 
 static bool is_multi(const lpb200_ctx *c) { return c && !c->shards.empty(); }
+
+// NCCL communicators are expensive to create (ncclCommInitAll: 0.5-3 s for 2-8 GPUs, plus the lazy connection set-up
+// of the first collective), contexts are cheap and the public API makes one per count matrix: communicators are
+// therefore kept per device list for the life of the process and lent to one context at a time.
+struct CommSet {
+    std::vector<int> devices;
+    std::vector<ncclComm_t> comms;
+    bool in_use = false;
+};
+static std::vector<CommSet *> g_comm_sets;
+static std::mutex g_comm_mutex;
+
+static CommSet *acquire_comms(const int *devices, int n) {
+    std::lock_guard<std::mutex> lock(g_comm_mutex);
+    std::vector<int> key(devices, devices + n);
+    for (CommSet *cs : g_comm_sets)
+        if (!cs->in_use && cs->devices == key) {
+            cs->in_use = true;
+            return cs;
+        }
+    NcclApi *nccl = nccl_api();
+    if (!nccl) return nullptr;
+    CommSet *cs = new CommSet();
+    cs->devices = key;
+    cs->comms.assign(n, nullptr);
+    if (nccl->CommInitAll(cs->comms.data(), n, devices) != ncclSuccess) {
+        delete cs;
+        return nullptr;
+    }
+    cs->in_use = true;
+    g_comm_sets.push_back(cs);
+    return cs;
+}
+static void release_comms(CommSet *cs) {
+    if (!cs) return;
+    std::lock_guard<std::mutex> lock(g_comm_mutex);
+    cs->in_use = false;
+}
 
 // contiguous gene ranges of near-equal size whose starts are multiples of LP_PI_BLOCK (as distributed.shard_bounds)
 static std::vector<int> shard_bounds(int G, int n) {
@@ -34,11 +73,23 @@ extern "C" lpb200_ctx *lpb200_create_multi(const int *devices, int n) {
     }
     // distinct devices: NCCL.  One device n times (n <= 8): the loopback communicator (lp_comm.cuh; testing).
     if (repeated && (!all_same || n > 8)) return nullptr;
-    NcclApi *nccl = repeated ? nullptr : nccl_api();
-    if (!repeated && !nccl) return nullptr;
+    const bool debug = getenv("LPB200_DEBUG") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!debug) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lpb200] create_multi: %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    CommSet *cs = nullptr;
+    if (!repeated) {
+        cs = acquire_comms(devices, n);
+        if (!cs) return nullptr;
+    }
+    lap("communicator");
     lpb200_ctx *parent = new lpb200_ctx();
     parent->device = devices[0];
-    std::vector<ncclComm_t> comms(n, nullptr);
+    parent->comm_set = cs;
     bool ok = true;
     for (int k = 0; k < n && ok; k++) {
         lpb200_ctx *c = lpb200_create(devices[k]);
@@ -47,9 +98,9 @@ extern "C" lpb200_ctx *lpb200_create_multi(const int *devices, int n) {
         if (cudaSetDevice(devices[k]) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
         else c->owns_stream = true;
     }
-    if (ok && nccl && nccl->CommInitAll(comms.data(), n, devices) != ncclSuccess) ok = false;
+    lap("shard contexts");
     if (!ok) {
-        for (ncclComm_t cm : comms) if (cm) nccl->CommDestroy(cm);
+        release_comms(cs);
         for (lpb200_ctx *c : parent->shards) lpb200_destroy(c);
         delete parent;
         return nullptr;
@@ -63,7 +114,8 @@ extern "C" lpb200_ctx *lpb200_create_multi(const int *devices, int n) {
         L->tmp_words.assign(n, 0);
     }
     for (int k = 0; k < n; k++) {
-        parent->shards[k]->comm = comms[k];
+        parent->shards[k]->comm = cs ? cs->comms[k] : nullptr;
+        parent->shards[k]->comm_borrowed = true;
         parent->shards[k]->loopback = L;
         parent->shards[k]->rank = k;
         parent->shards[k]->world = n;
