@@ -23,6 +23,8 @@ NA_COUNT = -1
 EXPAND_MEAN, EXPAND_DISP, EXPAND_DROP, EXPAND_POSTDROP, EXPAND_NORMDATA = 0, 1, 2, 3, 4
 EXPAND_NO_DEPTH, EXPAND_NO_BATCH = 16, 32
 
+KEEP_MU, KEEP_BATCH_MU, KEEP_DISP, KEEP_BATCH_DISP = 1, 2, 4, 8
+
 E_ARG, E_CUDA, E_STATE, E_NOTSUP, E_NONFINITE, E_COMM = -1, -2, -3, -4, -5, -6
 
 MU_MODELS = {"constant": MU_CONSTANT, "impulse": MU_IMPULSE, "splines": MU_SPLINES,
@@ -297,6 +299,8 @@ def declare_product_prototypes(lib):
         "lpb200_fit_pi": (C.c_int, [vp, P(Model), P(Params), P(Control), c_double_p, c_int32_p]),
         "lpb200_fit_model": (C.c_int, [vp, P(Model), P(Params), C.c_int, P(Control), C.c_double,
                                        c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_int32_p]),
+        "lpb200_fit_model_from": (C.c_int, [vp, P(Model), P(Params), C.c_int, P(Control), C.c_double, C.c_int,
+                                            c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p, c_int32_p]),
         "lpb200_fit_model_multi": (C.c_int, [vp, C.c_int, P(Model), P(Params), P(Control), C.c_double, c_double_p,
                                              c_double_p, c_int32_p, c_double_p, c_int32_p, P(C.c_uint64)]),
         "lpb200_post_drop": (C.c_int, [vp, P(Model), P(Params), c_int32_p, C.c_int, c_double_p]),

@@ -347,8 +347,6 @@ def fitModel(matCounts, dfAnnotation, vecConfoundersMu=None, vecConfoundersDisp=
              min_rowmean_global=float("nan")):
     """fitModel.R:137-356.  Returns the reference's list: lsMuModel, lsDispModel, lsDropModel,
     boolConvergenceModel, vecEMLogLikModel, strReport."""
-    if any(v is not None for v in (matMuModelInit, lsmatBatchModelInitMu, matDispModelInit, lsmatBatchModelInitDisp)):
-        raise LineagePulseError("warm-start hooks (mat*ModelInit) are not used by fitLPModels and are not implemented")
     counts = _as_counts(matCounts)
     G, N = counts.shape
     if vecNormConst is None:
@@ -371,8 +369,25 @@ def fitModel(matCounts, dfAnnotation, vecConfoundersMu=None, vecConfoundersDisp=
     p = A.ParamsData(design, model)
     if not boolFitDrop and model.drop_model != A.DROP_NONE:
         p.mat_drop = np.asfortranarray(lsDrop["matDropoutLinModel"], dtype=np.float64)
+    # warm-start hooks (fitModel.R:147-151; initialiseMuModel.R:93,131-133; initialiseDispModel.R:89,109-129)
+    keep = 0
+    if matMuModelInit is not None:
+        p.mat_mu = np.array(np.asarray(matMuModelInit, dtype=np.float64).reshape(G, -1), order="F", copy=True)
+        keep |= A.KEEP_MU
+    if lsmatBatchModelInitMu is not None and design.n_batches_mu:
+        p.batch_mu = [np.array(b, dtype=np.float64, order="F", copy=True) for b in lsmatBatchModelInitMu]
+        keep |= A.KEEP_BATCH_MU
+    if matDispModelInit is not None:
+        p.mat_disp = np.array(np.asarray(matDispModelInit, dtype=np.float64).reshape(G, -1), order="F", copy=True)
+        keep |= A.KEEP_DISP
+    if lsmatBatchModelInitDisp is not None and design.n_batches_disp:
+        p.batch_disp = [np.array(b, dtype=np.float64, order="F", copy=True) for b in lsmatBatchModelInitDisp]
+        keep |= A.KEEP_BATCH_DISP
+    for nm, a, want in (("matMuModelInit", p.mat_mu, design.n_mu_params(model)), ("matDispModelInit", p.mat_disp, design.n_disp_params(model))):
+        if a.shape != (G, want):
+            raise LineagePulseError(f"{nm} must be genes x model parameters ({G} x {want}), got {a.shape}")
     t0 = time.time()
-    r = eng.fit_model(model, p, boolFitDrop, ctl, min_rowmean_global)
+    r = eng.fit_model(model, p, boolFitDrop, ctl, min_rowmean_global, keep_mask=keep)
     dt = time.time() - t0
     _fill_models(design, model, p, lsMu, lsDisp, lsDrop, fill_drop=boolFitDrop)
     return _fit_result(lsMu, lsDisp, lsDrop, r, ctl.max_cycles if boolFitDrop else 1, dt, boolVerbose)

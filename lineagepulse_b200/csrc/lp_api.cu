@@ -112,8 +112,8 @@ static int multi_fit_mudisp_items(lpb200_ctx *ctx, const lpb200_model *m, lpb200
                                   double *ll_items, int32_t *conv_items, uint32_t *evals_items);
 static int multi_fit_pi(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, const lpb200_control *c, double *ll, int32_t *conv);
 static int multi_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop, const lpb200_control *c,
-                           double min_rowmean_global, double *em_ll, int32_t *n_iter, int32_t *converged, double *ll_init,
-                           double *ll, int32_t *conv);
+                           double min_rowmean_global, int keep_mask, double *em_ll, int32_t *n_iter, int32_t *converged,
+                           double *ll_init, double *ll, int32_t *conv);
 static int multi_fit_model_multi(lpb200_ctx *ctx, int n_jobs, const lpb200_model *models, lpb200_params *params,
                                  const lpb200_control *c, double min_rowmean_global, double *ll_init, double *em_ll,
                                  int32_t *converged, double *ll, int32_t *conv, uint64_t *ole);
@@ -1597,7 +1597,17 @@ static int sum_ll(lpb200_ctx *ctx, const double *ll, int G, double *out) {
 extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop,
                                 const lpb200_control *c, double min_rowmean_global, double *em_ll, int32_t *n_iter,
                                 int32_t *converged, double *ll_init, double *ll, int32_t *conv) {
-    if (is_multi(ctx)) return multi_fit_model(ctx, m, p, fit_drop, c, min_rowmean_global, em_ll, n_iter, converged, ll_init, ll, conv);
+    return lpb200_fit_model_from(ctx, m, p, fit_drop, c, min_rowmean_global, 0, em_ll, n_iter, converged, ll_init, ll, conv);
+}
+
+// fitModel with the reference's warm-start hooks (fitModel.R:147-151; initialiseMuModel.R:93,131-133,
+// initialiseDispModel.R:89,109-129): the matrices named in keep_mask are the caller's initial values
+// (matMuModelInit, lsmatBatchModelInitMu, matDispModelInit, lsmatBatchModelInitDisp); the others are initialised
+// as initMuModel / initDispModel do.
+extern "C" int lpb200_fit_model_from(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop,
+                                     const lpb200_control *c, double min_rowmean_global, int keep_mask, double *em_ll,
+                                     int32_t *n_iter, int32_t *converged, double *ll_init, double *ll, int32_t *conv) {
+    if (is_multi(ctx)) return multi_fit_model(ctx, m, p, fit_drop, c, min_rowmean_global, keep_mask, em_ll, n_iter, converged, ll_init, ll, conv);
     int rc = require_ready(ctx);
     if (rc) return rc;
     DevModel M;
@@ -1610,7 +1620,16 @@ extern "C" int lpb200_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_p
     if (fit_drop && M.drop_model == LPB200_DROP_NONE) fit_drop = 0;
     const int max_cycles = fit_drop ? c->max_cycles : 1;  // fitModel.R:181-183
     for (int k = 0; k < max_cycles; k++) em_ll[k] = NAN;
-    if ((rc = init_params_impl(ctx, M, p, min_rowmean_global, fit_drop != 0))) return rc;
+    {   // initial values; the warm-start matrices survive the initialisation
+        std::vector<double> keep[4];
+        double *mats[4] = {p->mat_mu, p->batch_mu, p->mat_disp, p->batch_disp};
+        const size_t sizes[4] = {(size_t)G * M.p_mu, (size_t)G * M.nbf_mu, (size_t)G * M.p_disp, (size_t)G * M.nbf_disp};
+        for (int k = 0; k < 4; k++)
+            if ((keep_mask >> k & 1) && mats[k]) keep[k].assign(mats[k], mats[k] + sizes[k]);
+        if ((rc = init_params_impl(ctx, M, p, min_rowmean_global, fit_drop != 0))) return rc;
+        for (int k = 0; k < 4; k++)
+            if (!keep[k].empty()) memcpy(mats[k], keep[k].data(), sizeof(double) * sizes[k]);
+    }
     if ((rc = eval_loglik_impl(ctx, M, p, ll))) return rc;  // :228-233
     double ll_new, ll_old = NAN;
     if ((rc = sum_ll(ctx, ll, G, &ll_new))) return rc;

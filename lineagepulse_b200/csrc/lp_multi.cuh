@@ -390,8 +390,8 @@ static int multi_fit_pi(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p
 }
 
 static int multi_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params *p, int fit_drop, const lpb200_control *c,
-                           double min_rowmean_global, double *em_ll, int32_t *n_iter, int32_t *converged, double *ll_init,
-                           double *ll, int32_t *conv) {
+                           double min_rowmean_global, int keep_mask, double *em_ll, int32_t *n_iter, int32_t *converged,
+                           double *ll_init, double *ll, int32_t *conv) {
     DevModel M;
     int rc = multi_model(ctx, m, M);
     if (rc) return rc;
@@ -406,8 +406,8 @@ static int multi_fit_model(lpb200_ctx *ctx, const lpb200_model *m, lpb200_params
     std::vector<double> li(n, NAN);
     rc = multi_run(ctx, [&](int k, lpb200_ctx *sc) {
         slice_params(ctx, M, p, k, sp[k], true);
-        return lpb200_fit_model(sc, m, &sp[k].p, fit_drop, c, mrm, em[k].data(), &it[k], &cv[k], &li[k], ll + ctx->bounds[k],
-                                conv + ctx->bounds[k]);
+        return lpb200_fit_model_from(sc, m, &sp[k].p, fit_drop, c, mrm, keep_mask, em[k].data(), &it[k], &cv[k], &li[k],
+                                     ll + ctx->bounds[k], conv + ctx->bounds[k]);
     });
     if (rc) return rc;
     for (int k = 0; k < n; k++) unslice_params(ctx, M, p, k, sp[k], true);

@@ -216,7 +216,8 @@ class Engine:
         params.sync_back()
         return dict(ll=ll, conv=conv)
 
-    def fit_model(self, model, params, fit_drop, control=None, min_rowmean_global=float("nan")):
+    def fit_model(self, model, params, fit_drop, control=None, min_rowmean_global=float("nan"), keep_mask=0):
+        """fitModel; ``keep_mask`` (_cabi.KEEP_* bits): matrices of ``params`` that are warm-start values."""
         control = control or A.default_control()
         G = self.n_genes
         em = np.full(control.max_cycles, np.nan)
@@ -225,9 +226,9 @@ class Engine:
         ll = np.zeros(G)
         conv = np.zeros(G, dtype=np.int32)
         ps = params.as_struct()
-        self._check(self.lib.lpb200_fit_model(self.ctx, C.byref(model), C.byref(ps), int(bool(fit_drop)),
-                                              C.byref(control), min_rowmean_global,
-                                              em.ctypes.data_as(A.c_double_p), C.byref(n_iter), C.byref(converged),
+        self._check(self.lib.lpb200_fit_model_from(self.ctx, C.byref(model), C.byref(ps), int(bool(fit_drop)),
+                                                   C.byref(control), min_rowmean_global, int(keep_mask),
+                                                   em.ctypes.data_as(A.c_double_p), C.byref(n_iter), C.byref(converged),
                                               C.byref(ll_init), ll.ctypes.data_as(A.c_double_p),
                                               conv.ctypes.data_as(A.c_int32_p)))
         params.sync_back()

@@ -186,3 +186,25 @@ def test_r_shim_compiles_and_links():
         err = C.create_string_buffer(512)
         assert lib.rs_released_context_raises(err) == 1
         assert b"no usable CUDA device" in err.value
+
+
+def test_test_dropout_table():
+    """testDropout (runHypothesisTests.R:179-214): LRT of the ZINB against the NB fits over the whole data set;
+    the drop-out model's parameters count as N x q for "PerCell", q for "AllCells" (the reference tests that
+    string although fitPi knows "ForAllCells": with "ForAllCells" nothing is added), NA rows are skipped."""
+    import pandas as pd
+    from scipy.stats import chi2
+    res = pd.DataFrame({"df_full_zinb": [8.0, 8.0, np.nan, 8.0], "df_full_nb": [8.0, 8.0, np.nan, 8.0],
+                        "loglik_full_zinb": [-100.0, -250.5, np.nan, -80.25], "loglik_full_nb": [-130.0, -300.0, np.nan, -99.0]})
+    for grp, extra in (("PerCell", 5 * 2), ("AllCells", 2), ("ForAllCells", 0)):
+        obj = lp.LineagePulseObject(dfResults=res, lsDropModel={"matDropoutLinModel": np.zeros((5, 2)),
+                                                              "lsDropModelGlobal": {"strDropFitGroup": grp}})
+        out = lp.testDropout(obj)
+        assert list(out.columns) == ["p", "df_delta", "deviance", "df_full", "df_red", "loglik_full", "loglik_red"]
+        row = out.iloc[0]
+        assert row["df_full"] == 24 + extra and row["df_red"] == 24 and row["df_delta"] == extra
+        assert row["loglik_full"] == -430.75 and row["loglik_red"] == -529.0 and row["deviance"] == 2 * (529.0 - 430.75)
+        if extra:
+            assert abs(row["p"] - chi2.sf(row["deviance"], extra)) <= 1e-12 * chi2.sf(row["deviance"], extra) + 1e-300
+        else:
+            assert row["p"] == 0.0   # pchisq(q > 0, df = 0, lower.tail = FALSE)
