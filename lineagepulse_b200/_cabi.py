@@ -290,6 +290,7 @@ def declare_product_prototypes(lib):
         "lpb200_load_counts_csc": (C.c_int, [vp, C.c_int, C.c_int, c_int32_p, c_int32_p, c_double_p]),
         "lpb200_load_counts_i32": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int]),
         "lpb200_set_design": (C.c_int, [vp, P(Design)]),
+        "lpb200_count_flags": (C.c_int, [vp, c_int32_p, c_int32_p, P(C.c_int64)]),
         "lpb200_init_params": (C.c_int, [vp, P(Model), P(Params), C.c_double]),
         "lpb200_eval_loglik": (C.c_int, [vp, P(Model), P(Params), c_double_p]),
         "lpb200_impulse_starts": (C.c_int, [vp, c_double_p, c_double_p]),

@@ -493,6 +493,7 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
     if dfAnnotation is None:
         raise LineagePulseError("Supply dfAnnotation.")
     sparse = sp.issparse(counts)
+    device_checks = False
     vals = counts.data if sparse else np.asarray(counts)
     if not np.issubdtype(vals.dtype, np.number):
         raise LineagePulseError("ERROR: counts contains non-numeric elements.")
@@ -504,8 +505,13 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
             raise LineagePulseError("ERROR: counts contains non-integer elements. Requires count data.")
         if np.any(fin < 0):
             raise LineagePulseError("ERROR: counts contains negative elements. Requires count data.")
-    elif vals.size and vals.min() < 0:   # one reduction pass instead of a comparison pass plus any()
-        raise LineagePulseError("ERROR: counts contains negative elements. Requires count data.")
+    else:
+        # dense int32 input without a cell filter: the negative check and the all-zero gene / cell filters are read off
+        # the uploaded matrix (lpb200_count_flags) instead of three host passes over G x N
+        device_checks = (not sparse and isinstance(counts, np.ndarray) and counts.dtype == np.int32 and counts.flags.c_contiguous
+                         and counts.size > 0)
+        if not device_checks and vals.size and vals.min() < 0:   # one reduction pass instead of a comparison pass plus any()
+            raise LineagePulseError("ERROR: counts contains negative elements. Requires count data.")
     for name, v in (("boolVerbose", boolVerbose), ("boolSuperVerbose", boolSuperVerbose)):
         if not isinstance(v, (bool, np.bool_)):
             raise LineagePulseError(f"ERROR IN INPUT DATA CHECK: {name} must be logical (TRUE or FALSE).")
@@ -559,7 +565,24 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
         ptok = ~np.isnan(dfAnnotation["continuous"].astype(np.float64))
         strReport += f"# {int((~ptok).sum())} out of {N} cells did not have a continuous covariate and were excluded.\n"
         keep_cells &= ptok
-    if sparse:
+    cm_dev = None
+    if device_checks and keep_cells.all():
+        from .engine import LPB200Error
+        try:
+            cm_dev = CountMatrix(dense, rownames, colnames, device, devices)
+            rs, cs, n_neg = cm_dev.engine().count_flags()
+        except LPB200Error:      # no device here: the input is still validated (on the host); any fit will fail loudly
+            cm_dev, device_checks = None, False
+            if vals.min() < 0:
+                raise LineagePulseError("ERROR: counts contains negative elements. Requires count data.")
+    if cm_dev is not None:
+        m = dense
+        if n_neg > 0:
+            cm_dev.engine().close()
+            raise LineagePulseError("ERROR: counts contains negative elements. Requires count data.")
+    elif device_checks and vals.min() < 0:
+        raise LineagePulseError("ERROR: counts contains negative elements. Requires count data.")
+    elif sparse:
         m = counts.tocsc()[:, keep_cells]
         rs = np.asarray(m.sum(axis=1)).ravel()
         cs = np.asarray(m.sum(axis=0)).ravel()
@@ -579,13 +602,19 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
         m = m.tocsr()[gene_idx, :].tocsc()[:, vecboolCells]
     elif not (vecboolGenes.all() and vecboolCells.all()):
         m = np.ascontiguousarray(m[gene_idx][:, vecboolCells])  # otherwise: no copy, H2D straight from the caller's buffer
+        if cm_dev is not None:      # the uploaded matrix had all-zero rows / columns: upload the filtered one instead
+            cm_dev.engine().close()
+            cm_dev = None
     dfProc = {k: v[cell_idx] for k, v in dfAnnotation.items()}
     if "cell" not in dfProc:
         dfProc["cell"] = colnames[cell_idx]
     if boolVerbose:
         message(strReport.rstrip("\n"))
+    if cm_dev is not None:
+        cm_dev.rownames, cm_dev.colnames = rownames[gene_idx], colnames[cell_idx]
     objLP = LineagePulseObject(
-        dfAnnotationProc=dfProc, matCountsProc=CountMatrix(m, rownames[gene_idx], colnames[cell_idx], device, devices),
+        dfAnnotationProc=dfProc,
+        matCountsProc=cm_dev if cm_dev is not None else CountMatrix(m, rownames[gene_idx], colnames[cell_idx], device, devices),
         scaDFSplinesDisp=scaDFSplinesDisp, scaDFSplinesMu=scaDFSplinesMu, strReport=strReport,
         vecAllGenes=rownames, vecConfoundersMu=vecConfoundersMu, vecConfoundersDisp=vecConfoundersDisp)
     return {"objLP": objLP,

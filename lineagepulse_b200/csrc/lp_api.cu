@@ -31,6 +31,8 @@ struct lpb200_ctx {
     uint32_t *d_perm = nullptr;   // [G][pitch] non-zero cells first, then zeros
     int32_t *d_nnz = nullptr, *d_nobs = nullptr;
     std::vector<double> row_means;
+    std::vector<int32_t> row_max, col_max;   // per gene / per cell largest count (all-zero filters of processSCData)
+    unsigned long long n_negative = 0;       // entries < 0 (NA markers included)
     int global_max = 0;
     // design
     bool have_design = false;
@@ -470,10 +472,21 @@ static int finish_counts(lpb200_ctx *ctx, TmpCounts &tmp, int G, int N, size_t p
     CK(cudaMalloc((void **)&ctx->d_nobs, sizeof(int32_t) * G));
     build_perm_kernel<<<G, 256, 0, ctx->stream>>>(d_i32, G, N, pitch, ctx->d_perm, ctx->d_nnz, ctx->d_nobs);
     CK(cudaGetLastError());
+    DevBuf<int32_t> d_colmax;
+    DevBuf<unsigned long long> d_neg;
+    CK(d_colmax.alloc(N));
+    CK(d_neg.alloc(1));
+    CK(cudaMemsetAsync(d_neg.p, 0, sizeof(unsigned long long), ctx->stream));
+    col_stats_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(d_i32, G, N, pitch, d_colmax.p, d_neg.p);
+    CK(cudaGetLastError());
     ctx->row_means.resize(G);
-    std::vector<int32_t> xmax(G);
+    ctx->row_max.resize(G);
+    ctx->col_max.resize(N);
+    std::vector<int32_t> &xmax = ctx->row_max;
     CK(cudaMemcpyAsync(ctx->row_means.data(), d_mean.p, sizeof(double) * G, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(xmax.data(), ctx->d_xmax, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->col_max.data(), d_colmax.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->n_negative, d_neg.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->global_max = 0;
     for (int v : xmax) ctx->global_max = std::max(ctx->global_max, v);
@@ -496,8 +509,30 @@ static int finish_counts(lpb200_ctx *ctx, TmpCounts &tmp, int G, int N, size_t p
     ctx->G = G;
     ctx->N = N;
     ctx->pitch = pitch;
-    ctx->stats.launches += 3;
+    ctx->stats.launches += 4;
     ctx->have_starts = false;
+    return 0;
+}
+
+extern "C" int lpb200_count_flags(lpb200_ctx *ctx, int32_t *gene_max, int32_t *cell_max, int64_t *n_negative) {
+    if (!ctx) return LPB200_E_CUDA;
+    if (is_multi(ctx)) {
+        if (ctx->bounds.empty()) return set_err(ctx, LPB200_E_STATE, "counts not loaded");
+        if (n_negative) *n_negative = 0;
+        if (cell_max) std::fill(cell_max, cell_max + ctx->N, 0);
+        for (size_t k = 0; k < ctx->shards.size(); k++) {
+            const lpb200_ctx *c = ctx->shards[k];
+            if (gene_max) memcpy(gene_max + ctx->bounds[k], c->row_max.data(), sizeof(int32_t) * c->G);
+            if (cell_max)
+                for (int j = 0; j < ctx->N; j++) cell_max[j] = std::max(cell_max[j], c->col_max[j]);
+            if (n_negative) *n_negative += (int64_t)c->n_negative;
+        }
+        return 0;
+    }
+    if (!ctx->d_counts) return set_err(ctx, LPB200_E_STATE, "counts not loaded");
+    if (gene_max) memcpy(gene_max, ctx->row_max.data(), sizeof(int32_t) * ctx->G);
+    if (cell_max) memcpy(cell_max, ctx->col_max.data(), sizeof(int32_t) * ctx->N);
+    if (n_negative) *n_negative = (int64_t)ctx->n_negative;
     return 0;
 }
 

@@ -1118,6 +1118,22 @@ __global__ void row_stats_kernel(const int32_t *c, int G, int N, size_t pitch, d
     }
 }
 
+// per cell: largest count over this shard's genes (NA skipped); per launch: number of negative entries (the NA marker -1
+// included) -- the input checks and the all-zero cell filter of processSCData.R:102-112,276-289 on the uploaded matrix
+__global__ void col_stats_kernel(const int32_t *c, int G, int N, size_t pitch, int32_t *colmax, unsigned long long *n_negative) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    int mx = 0;
+    unsigned long long neg = 0;
+    for (int g = 0; g < G; g++) {
+        const int v = c[(size_t)g * pitch + j];
+        mx = max(mx, v);
+        neg += (v < 0);
+    }
+    colmax[j] = mx;
+    if (neg) atomicAdd(n_negative, neg);
+}
+
 __global__ void narrow_u16_kernel(const int32_t *in, uint16_t *out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -140,6 +140,13 @@ class Engine:
         self._check(self.lib.lpb200_set_design(self.ctx, C.byref(design.struct)))
         self.design = design
 
+    def count_flags(self):
+        """(largest count per gene, largest count per cell, number of negative entries) of the uploaded matrix."""
+        gm, cm = np.zeros(self.n_genes, dtype=np.int32), np.zeros(self.n_cells, dtype=np.int32)
+        neg = C.c_int64()
+        self._check(self.lib.lpb200_count_flags(self.ctx, gm.ctypes.data_as(A.c_int32_p), cm.ctypes.data_as(A.c_int32_p), C.byref(neg)))
+        return gm, cm, int(neg.value)
+
     def row_means(self):
         out = np.zeros(self.n_genes)
         self._check(self.lib.lpb200_row_means(self.ctx, out.ctypes.data_as(A.c_double_p)))
