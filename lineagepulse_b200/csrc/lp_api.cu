@@ -66,36 +66,16 @@ struct lpb200_ctx {
     int use_table = 1;
     int no_fastpath = 0;   // LPB200_NO_FASTPATH=1: always run the generic evaluator (testing)
     int ctas_per_sm = LP_FAST_MINBLOCKS;  // persistent fit CTAs per SM (LPB200_CTAS_PER_SM overrides)
-    int cluster = 0;       // CTAs per work item of the fit kernel; 0: chosen per launch (LPB200_CLUSTER = 1 | 2 | 4 overrides)
+    int cluster = 0;       // CTAs per work item of the fit kernel; 0: chosen per launch (LPB200_CLUSTER = 1 | 2 overrides)
 };
 
-// The fit-kernel variants: count type (uint16_t / int32_t) x evaluator (generic; constant or impulse mean x NB or ZINB)
-// x launched as thread-block clusters or not.
-typedef void (*FitKernelFn)(const FitArgs);
-template <typename CT, bool CL>
-static FitKernelFn fit_kernel_ct(int variant) {
-    switch (variant) {
-    case 1: return fit_mudisp_kernel<CT, LP_MU_FAST_CONST, false, CL>;
-    case 2: return fit_mudisp_kernel<CT, LP_MU_FAST_CONST, true, CL>;
-    case 3: return fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, false, CL>;
-    case 4: return fit_mudisp_kernel<CT, LP_MU_FAST_IMPULSE, true, CL>;
-    default: break;
-    }
-    if (!CL) {   // the covariate-model kernels are built for one CTA per item only
-        switch (variant) {
-        case 5: return fit_mudisp_kernel<CT, LP_MU_FAST_GROUPS, false, false>;
-        case 6: return fit_mudisp_kernel<CT, LP_MU_FAST_GROUPS, true, false>;
-        case 7: return fit_mudisp_kernel<CT, LP_MU_FAST_SPLINES, false, false>;
-        case 8: return fit_mudisp_kernel<CT, LP_MU_FAST_SPLINES, true, false>;
-        default: break;
-        }
-    }
-    return fit_mudisp_kernel<CT, -1, false, CL>;
-}
-#define LP_N_FIT_VARIANTS 9
+// The fit-kernel variants: count type (uint16_t / int32_t) x evaluator (generic; constant or impulse mean x NB or ZINB;
+// groups or splines mean x NB or ZINB) x launched as thread-block clusters or not.  They are instantiated in two
+// translation units of their own (lp_fit_u16.cu, lp_fit_i32.cu: see lp_fit_table.cuh) so that the library builds in
+// parallel.
+#include "lp_fit_table.cuh"
 static FitKernelFn fit_kernel(bool u16, int variant, bool cl) {
-    if (u16) return cl ? fit_kernel_ct<uint16_t, true>(variant) : fit_kernel_ct<uint16_t, false>(variant);
-    return cl ? fit_kernel_ct<int32_t, true>(variant) : fit_kernel_ct<int32_t, false>(variant);
+    return u16 ? lp_fit_kernel_u16(variant, cl) : lp_fit_kernel_i32(variant, cl);
 }
 static size_t fit_smem_bytes(bool cl) { return cl ? sizeof(FitSharedT<true>) : sizeof(FitSharedT<false>); }
 
@@ -276,7 +256,7 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
     e = getenv("LPB200_NO_FASTPATH");
     if (e && atoi(e)) c->no_fastpath = 1;
     e = getenv("LPB200_CLUSTER");
-    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) c->cluster = atoi(e);
+    if (e && (atoi(e) == 1 || atoi(e) == 2)) c->cluster = atoi(e);
     return c;
 }
 
@@ -1059,16 +1039,14 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     // the item-length tail of the dynamic queue -- by the cluster size; the result does not depend on it
     // (virtual-warp summation order, lp_kernels.cuh).  Measured (profiles/README.md): it pays when a launch has few
     // items per CTA slot (592 genes x 100 000 cells: -9 % with 2 CTAs per item); with 25 items per slot the
-    // concurrent B / C / D launches already back-fill each other's tails and 4 CTAs per item cost 10 % (fewer
-    // co-resident clusters, redundant state machines).  Short rows stay with one CTA per item: the cluster barrier
-    // per evaluation would show against a 20-40 us pass.
+    // concurrent B / C / D launches already back-fill each other's tails (2 CTAs per item: +-0 %, 4: +10 %).
+    // Short rows stay with one CTA per item: the cluster barrier per evaluation would show against a 20-40 us pass.
     int cluster = ctx->cluster;
     if (cluster == 0) {
         const size_t slots = (size_t)ctx->sm_count * ctx->ctas_per_sm;
-        cluster = 1;
-        if (N >= 32768 && J.n_items < 8 * slots) cluster = 2;
-        if (N >= 65536 && J.n_items < 3 * slots) cluster = 4;
+        cluster = (N >= 32768 && J.n_items < 8 * slots) ? 2 : 1;
     }
+    cluster = std::min(cluster, LP_MAX_CLUSTER);
     if (threads != LP_FIT_THREADS) cluster = 1;
     const bool cl = cluster > 1;
     const size_t smem = fit_smem_bytes(cl);

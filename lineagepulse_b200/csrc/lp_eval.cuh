@@ -14,7 +14,11 @@
 #define LP_TAB 1024       // entries of one (x, phi) table
 #endif
 #define LP_NTAB 3         // tables per pass: base phi, phi + eps, phi - eps
-#define LP_VW 64          // virtual warps of the evaluation layout (see lp_kernels.cuh): fixes the summation order
+#ifdef LP_VW_OVERRIDE     // timing experiments only (profiles/README.md); changes the summation order
+#define LP_VW LP_VW_OVERRIDE
+#else
+#define LP_VW 32          // virtual warps of the evaluation layout (see lp_kernels.cuh): fixes the summation order
+#endif
 
 #define LP_MU_FAST_CONST 0
 #define LP_MU_FAST_IMPULSE 1
@@ -48,7 +52,7 @@ LP_HD double lp_base_phi(const double *b) { return lp_clamp(lp_exp(b[0]), LP_CLA
 LP_HD int lp_request_ntabs(int req, int base) { return (req == LP_REQ_F) ? 1 : (base == 0 ? 3 : 1); }
 
 #ifdef __CUDACC__
-__host__ __device__ __noinline__ double lp_nb_xphi_part_cold(double x, double phi) { return lp_nb_xphi_part(x, phi); }
+static __host__ __device__ __noinline__ double lp_nb_xphi_part_cold(double x, double phi) { return lp_nb_xphi_part(x, phi); }
 #else
 inline double lp_nb_xphi_part_cold(double x, double phi) { return lp_nb_xphi_part(x, phi); }
 #endif

@@ -1,0 +1,6 @@
+// fit_mudisp_kernel for uint16_t counts (see lp_fit_table.cuh)
+#define LP_FIT_TABLE_COUNT_TYPE 1
+#include "lp_fit_table.cuh"
+FitKernelFn lp_fit_kernel_u16(int variant, bool cluster) {
+    return cluster ? fit_kernel_ct<uint16_t, true>(variant) : fit_kernel_ct<uint16_t, false>(variant);
+}

@@ -58,8 +58,8 @@ static const double lp_sferr_host[31] = LP_SFERR_VALUES;
 #define LP_ODD_RECIP_VALUES {1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0}
 static const double lp_odd_recip_host[9] = LP_ODD_RECIP_VALUES;
 #ifdef __CUDACC__
-__constant__ double lp_sferr_dev[31] = LP_SFERR_VALUES;
-__constant__ double lp_odd_recip_dev[9] = LP_ODD_RECIP_VALUES;
+static __constant__ double lp_sferr_dev[31] = LP_SFERR_VALUES;
+static __constant__ double lp_odd_recip_dev[9] = LP_ODD_RECIP_VALUES;
 #endif
 
 // log1p and lgamma of the table-building code.  Not the CUDA library's: own routines over lp_log and IEEE
@@ -179,9 +179,9 @@ LP_HD double lp_nb_mu_part(double x, double mu, double phi) {
 // evalLogLikMatrix reach it: a cold function, tested by the callers that can see such a phi.
 LP_HD bool lp_nb_small_x(double x, double phi) { return x < 1e-10 * phi; }
 #ifdef __CUDACC__
-__host__ __device__ __noinline__
+static __host__ __device__ __noinline__
 #else
-inline
+static inline
 #endif
 double lp_dnbinom_small_x(double x, double mu, double phi) {
     const double p = (phi < mu) ? lp_log(phi / (1.0 + phi / mu)) : lp_log(mu / (1.0 + mu / phi));

@@ -15,7 +15,7 @@ def pytest_configure(config):
     lib = os.path.join(ROOT, "lineagepulse_b200", "liblpb200.so")
     if not os.path.exists(lib):
         import subprocess
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "lineagepulse_b200", "csrc")],
+        subprocess.check_call(["make", "-j", "4", "-C", os.path.join(ROOT, "lineagepulse_b200", "csrc")],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 

@@ -9,7 +9,7 @@
 //   lp_bfgs.cuh    the resumable vmmin
 // What is restated here: the kernel's evaluation layout -- lane-per-point / cells-per-warp slots, the
 // stride of the cell loop over the gene's (non-zero first) cell permutation, the xor-shuffle reduction inside a
-// (virtual) warp and the index-order reduction across the 64 virtual warps -- i.e. the ORDER in which the same
+// (virtual) warp and the index-order reduction across the LP_VW virtual warps -- i.e. the ORDER in which the same
 // doubles are added (independent of the CTA size and of the cluster size the kernel is launched with).
 // tests/test_gpu_parity.py::test_fit_kernel_equals_host_mirror_bitwise asserts that kernel and mirror agree
 // bit for bit on every (gene, start) item.  Not part of the product; nothing in lineagepulse_b200/ links it.
@@ -97,7 +97,7 @@ static void eval_points(const Ctx &C, Shared &S, const GeneView &g, int gene, in
     int npad = 1;
     while (npad < nk) npad <<= 1;
     const int cpw = 32 / npad, stride = LP_VW * cpw;
-    // virtual warp v, slot s: cells r = v cpw + s + i 64 cpw of the gene's permutation, added in that order;
+    // virtual warp v, slot s: cells r = v cpw + s + i LP_VW cpw of the gene's permutation, added in that order;
     // which physical warp / CTA of a cluster runs v is immaterial (lp_kernels.cuh)
     double red[LP_VW][LP_KC];
     for (int v = 0; v < LP_VW; v++) {

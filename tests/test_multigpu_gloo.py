@@ -88,3 +88,49 @@ def test_shard_bounds():
     assert all(x % 16 == 0 for x in b[:-1])          # shards start on summation-block boundaries
     assert max(np.diff(b)) - min(np.diff(b)) <= 16
     assert shard_bounds(10, 4) == [0, 10, 10, 10, 10]  # fewer blocks than shards: trailing shards are empty
+
+
+def _comm_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import ctypes as C
+    import torch.distributed as dist
+    from lineagepulse_b200 import _cabi as A
+    from lineagepulse_b200.distributed import init_comm
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib = A.load_library()
+
+        class FakeEngine:   # the two calls init_comm makes; the real ones need a GPU (lpb200_comm_init = ncclCommInitRank)
+            def comm_unique_id(self):
+                buf = C.create_string_buffer(A.UNIQUE_ID_BYTES)
+                assert lib.lpb200_comm_unique_id(buf) == 0      # the library's own NCCL binding (dlopen), no GPU needed
+                return buf.raw
+
+            def init_comm(self, r, w, uid):
+                self.got = (r, w, uid)
+
+        e = FakeEngine()
+        r, w = init_comm(e)
+        out.put((rank, r, w, e.got[0], e.got[1], e.got[2]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_library_communicator_bootstrap_world2():
+    """One process per GPU: rank 0 creates the NCCL unique id inside the library, torch.distributed only carries its
+    128 bytes; every rank hands the same id with its own rank to lpb200_comm_init (distributed.init_comm)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_comm_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(r[0], r[1], r[2], r[3], r[4]) for r in res] == [(0, 0, 2, 0, 2), (1, 1, 2, 1, 2)]
+    assert res[0][5] == res[1][5] and len(res[0][5]) == 128 and any(res[0][5])
