@@ -1058,12 +1058,13 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     const bool fast_base = !ctx->no_fastpath && lp_disp_is_scalar(D, M) &&
                            (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
     const bool fast_ci = fast_base && D.n_conf_mu == 0 && (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE);
-    const bool fast_cov = fast_base && !fast_ci && (M.mu_model == LPB200_MU_GROUPS || M.mu_model == LPB200_MU_SPLINES);
+    const bool fast_cov = fast_base && !fast_ci && (M.mu_model == LPB200_MU_GROUPS || M.mu_model == LPB200_MU_SPLINES ||
+                                                    M.mu_model == LPB200_MU_CONSTANT);   // constant: with mean batch factors
     if (fast_cov) cluster = 1;
     const bool fast = fast_ci || fast_cov;
     const int zinb_bit = (M.drop_model == LPB200_DROP_LOGISTIC) ? 1 : 0;
     const int variant = fast_ci ? (M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) + zinb_bit
-                                : (fast_cov ? (M.mu_model == LPB200_MU_GROUPS ? 5 : 7) + zinb_bit : 0);
+                                : (fast_cov ? (M.mu_model == LPB200_MU_GROUPS ? 5 : (M.mu_model == LPB200_MU_SPLINES ? 7 : 9)) + zinb_bit : 0);
     FitKernelFn kernel = fit_kernel(ctx->is_u16, variant, cl);
     CK(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * per_sm);

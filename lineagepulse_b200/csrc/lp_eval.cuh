@@ -24,6 +24,7 @@
 #define LP_MU_FAST_IMPULSE 1
 #define LP_MU_FAST_GROUPS 2     // group means + mean batch factors (C4)
 #define LP_MU_FAST_SPLINES 3    // spline mean model + mean batch factors (C5)
+#define LP_MU_FAST_CONSTCOV 4   // constant mean + mean batch factors (the H0 fits of C4)
 
 // entries of each (x, phi) table of a pass over N cells with nk points, or 0: tabulate when that is cheaper
 // than N x nk evaluations of lp_nb_xphi_part

@@ -204,7 +204,7 @@ struct CovariateLane {
     __device__ __forceinline__ Pre preload(int r, int j) const {
         Pre p;
         p.x = (r < nnz) ? lp_load_count(row, j) : 0;
-        p.g = (MUK == LPB200_MU_GROUPS) ? D->group[j] : 0;
+        p.g = (MUK == LPB200_MU_GROUPS) ? D->group[j] : 0;   // constant mean with batch factors: MUK == LPB200_MU_CONSTANT
         p.b0 = (D->n_conf_mu > 0) ? D->bidx_mu[j] : 0;
         return p;
     }
@@ -212,7 +212,7 @@ struct CovariateLane {
         const int x = pre.x;
         const int N = D->N;
         double mu;
-        if (MUK == LPB200_MU_GROUPS) {
+        if (MUK == LPB200_MU_GROUPS || MUK == LPB200_MU_CONSTANT) {
             mu = P->mu[pre.g];
         } else {
             double lin = 0.0;
@@ -441,6 +441,8 @@ fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
                     lp_eval_points<CL, CovariateLane<CT, LPB200_MU_GROUPS, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
                 else if constexpr (MU == LP_MU_FAST_SPLINES)
                     lp_eval_points<CL, CovariateLane<CT, LPB200_MU_SPLINES, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
+                else if constexpr (MU == LP_MU_FAST_CONSTCOV)
+                    lp_eval_points<CL, CovariateLane<CT, LPB200_MU_CONSTANT, ZINB>>(A, S, row, gene, xmax, kc, ntabs, true, S.vals + base, pi_ptr, l1m_ptr);
                 else
                     lp_eval_points<CL, GenericLane<CT>>(A, S, row, gene, xmax, kc, ntabs, scalar_phi, S.vals + base, pi_ptr, l1m_ptr);
             }

@@ -3,8 +3,9 @@
 #include "lp_fit_kernel.cuh"
 
 typedef void (*FitKernelFn)(const FitArgs);
-#define LP_N_FIT_VARIANTS 9
-// variant: 0 generic; 1 / 2 constant mean NB / ZINB; 3 / 4 impulse NB / ZINB; 5 / 6 groups NB / ZINB; 7 / 8 splines NB / ZINB
+#define LP_N_FIT_VARIANTS 11
+// variant: 0 generic; 1 / 2 constant mean NB / ZINB; 3 / 4 impulse NB / ZINB; 5 / 6 groups NB / ZINB; 7 / 8 splines NB / ZINB;
+// 9 / 10 constant mean with batch factors NB / ZINB
 FitKernelFn lp_fit_kernel_u16(int variant, bool cluster);
 FitKernelFn lp_fit_kernel_i32(int variant, bool cluster);
 
@@ -24,6 +25,8 @@ static FitKernelFn fit_kernel_ct(int variant) {
         case 6: return fit_mudisp_kernel<CT, LP_MU_FAST_GROUPS, true, false>;
         case 7: return fit_mudisp_kernel<CT, LP_MU_FAST_SPLINES, false, false>;
         case 8: return fit_mudisp_kernel<CT, LP_MU_FAST_SPLINES, true, false>;
+        case 9: return fit_mudisp_kernel<CT, LP_MU_FAST_CONSTCOV, false, false>;
+        case 10: return fit_mudisp_kernel<CT, LP_MU_FAST_CONSTCOV, true, false>;
         default: break;
         }
     }
