@@ -406,8 +406,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a host-side group: ranks that wait while rank 0 drives all GPUs (the e2e leg) must not wait inside an NCCL
+        # barrier -- its kernel would spin on the very GPUs rank 0 is using from another process
+        cpu_group = dist.new_group(backend="gloo")
     stream = torch.cuda.current_stream()
 
     genes, cells, h1, desc = CONFIGS[args.config]
@@ -517,8 +521,9 @@ def main():
     del flush
     torch.cuda.empty_cache()
     if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, X)
+        torch.cuda.synchronize()
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(X, parts, dst=0, group=cpu_group)
         X_all = np.concatenate(parts, 0) if rank == 0 else None
         del parts
     else:
@@ -562,6 +567,9 @@ def main():
         h2d = int(X_all.nbytes + 8 * N * 6 * world)  # counts + pseudotime + 4-column impulse basis + size factors, per device
         d2h = int(obj.dfResults.shape[0] * 14 * 8 + 8 * Gt * (7 + 1 + 1 + 1) * 2 + 8 * N)  # results table, parameter matrices, drop-out model
         del flush
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)     # host-side wait (gloo): the other ranks' GPUs stay idle while rank 0 uses them
     barrier()
 
     # ---- the north_star matrix once: strong scaling ---------------------------------------------
