@@ -2,6 +2,7 @@
 // (fitMuDisp, fitPi, evalLogLikMatrix, fitModel's EM loop) and the LRT.  No CPU fallback: every
 // compute entry point needs a CUDA device and fails with LPB200_E_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -103,6 +104,20 @@ static int multi_expand_fits(lpb200_ctx *ctx, const lpb200_model *m, const lpb20
                              int what, double *z);
 static int multi_get_stats(lpb200_ctx *ctx, lpb200_stats *s);
 static void release_comms(struct CommSet *cs);
+
+// LPB200_DEBUG: host wall-clock of the phases of a call
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char *scope;
+    explicit PhaseTimer(const char *scope_) : on(getenv("LPB200_DEBUG") != nullptr), t0(std::chrono::steady_clock::now()), scope(scope_) {}
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lpb200] %s: %s %.2f ms\n", scope, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static int set_err(lpb200_ctx *c, int code, const char *fmt, ...) {
     char buf[512];
@@ -1364,6 +1379,7 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     A.ndeps = c->ndeps;
     const int nb = (N + 127) / 128;
     int rc;
+    PhaseTimer pt("fit_pi");
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
 
     if (drop_fit_group == LPB200_DROPFIT_PERCELL) {
@@ -1395,6 +1411,11 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
             int active = 0;
             CK(cudaMemcpyAsync(&active, d_active.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
+            if (pt.on) {
+                char buf[64];
+                snprintf(buf, sizeof buf, "round %ld (%d cells active)", round, active);
+                pt.lap(buf);
+            }
             if (active == 0) break;
             if (round >= 8) check_every = 4;
             if (active <= tail_threshold) {
@@ -1412,6 +1433,7 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
                 break;
             }
         }
+        pt.lap("tail");
         CK(d_ll.alloc(N));
         CK(d_conv.alloc(N));
         CK(d_evals.alloc(N));
@@ -1425,6 +1447,7 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
         CK(cudaMemcpyAsync(evals.data(), d_evals.p, sizeof(unsigned) * N, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        pt.lap("results");
         bool nonfinite = false;
         for (int j = 0; j < N; j++) {
             ctx->stats.fn_evals += evals[j];
@@ -1634,6 +1657,7 @@ extern "C" int lpb200_fit_model_from(lpb200_ctx *ctx, const lpb200_model *m, lpb
     if (fit_drop && M.drop_model == LPB200_DROP_NONE) fit_drop = 0;
     const int max_cycles = fit_drop ? c->max_cycles : 1;  // fitModel.R:181-183
     for (int k = 0; k < max_cycles; k++) em_ll[k] = NAN;
+    PhaseTimer pt("fit_model");
     {   // initial values; the warm-start matrices survive the initialisation
         std::vector<double> keep[4];
         double *mats[4] = {p->mat_mu, p->batch_mu, p->mat_disp, p->batch_disp};
@@ -1644,17 +1668,21 @@ extern "C" int lpb200_fit_model_from(lpb200_ctx *ctx, const lpb200_model *m, lpb
         for (int k = 0; k < 4; k++)
             if (!keep[k].empty()) memcpy(mats[k], keep[k].data(), sizeof(double) * sizes[k]);
     }
+    pt.lap("initial values");
     if ((rc = eval_loglik_impl(ctx, M, p, ll))) return rc;  // :228-233
     double ll_new, ll_old = NAN;
     if ((rc = sum_ll(ctx, ll, G, &ll_new))) return rc;
     if (ll_init) *ll_init = ll_new;
+    pt.lap("initial log-likelihood");
     int iter = 1;
     std::vector<double> pill(fit_drop ? N : 1);
     std::vector<int32_t> piconv(fit_drop ? N : 1);
     int any_nonconv = 0;
     while (iter == 1 || (ll_new > ll_old * c->prec_em && iter <= max_cycles)) {  // :242-243
         if (fit_drop && (rc = fit_pi_impl(ctx, M, m->drop_fit_group, p, c, pill.data(), piconv.data()))) return rc;
+        pt.lap("fitPi");
         if ((rc = sync_error(ctx, fit_mudisp_impl(ctx, M, p, c, ll, conv)))) return rc;
+        pt.lap("fitMuDisp");
         ll_old = ll_new;
         if ((rc = sum_ll(ctx, ll, G, &ll_new))) return rc;
         em_ll[iter - 1] = ll_new;
