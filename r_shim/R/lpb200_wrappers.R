@@ -165,8 +165,11 @@ fitModel <- function(matCounts, dfAnnotation, vecConfoundersMu = NULL, vecConfou
                                      lsDropModel = lsDropModel, strDropModel = strDropModel,
                                      strDropFitGroup = strDropFitGroup, MAXIT_BFGS_Pi = 10000, RELTOL_BFGS_Pi = 10^(-8))
     ctx <- lpSetDesign(lpContext(matCounts), lpDesign(matCounts, lsMuModel, lsDispModel, lsDropModel))
+    ## warm-start hooks (fitModel.R:147-151): which of the matrices are the caller's initial values
+    scaKeepMask <- 1L * !is.null(matMuModelInit) + 2L * !is.null(lsmatBatchModelInitMu) +
+        4L * !is.null(matDispModelInit) + 8L * !is.null(lsmatBatchModelInitDisp)
     res <- .Call("lp_fit_model", ctx, lpModel(lsMuModel, lsDispModel, lsDropModel),
-                 lpParams(lsMuModel, lsDispModel, lsDropModel), boolFitDrop, nrow(matCounts))
+                 lpParams(lsMuModel, lsDispModel, lsDropModel), boolFitDrop, nrow(matCounts), as.integer(scaKeepMask))
     p <- res[[1]]; info <- res[[5]]
     rownames(p$matMuModel) <- rownames(matCounts); rownames(p$matDispModel) <- rownames(matCounts)
     lsMuModel$matMuModel <- p$matMuModel

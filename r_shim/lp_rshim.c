@@ -182,8 +182,10 @@ SEXP lp_fit_pi(SEXP sctx, SEXP model, SEXP params, SEXP n_out) {
     return out;
 }
 
-/* ---- fitModel (fitModel.R:137): whole EM loop in one call ----------------------------------- */
-SEXP lp_fit_model(SEXP sctx, SEXP model, SEXP params, SEXP fit_drop, SEXP n_genes) {
+/* ---- fitModel (fitModel.R:137): whole EM loop in one call -----------------------------------
+ * keep_mask: LPB200_KEEP_* bits of the parameter matrices that are warm starts (matMuModelInit, lsmatBatchModelInitMu,
+ * matDispModelInit, lsmatBatchModelInitDisp, fitModel.R:147-151); 0 = the library initialises everything */
+SEXP lp_fit_model(SEXP sctx, SEXP model, SEXP params, SEXP fit_drop, SEXP n_genes, SEXP keep_mask) {
     lpb200_ctx *ctx = ctx_of(sctx);
     lpb200_model m = model_of(model);
     lpb200_params p = params_of(params);
@@ -194,8 +196,8 @@ SEXP lp_fit_model(SEXP sctx, SEXP model, SEXP params, SEXP fit_drop, SEXP n_gene
     SEXP conv = PROTECT(allocVector(INTSXP, G)), info = PROTECT(allocVector(REALSXP, 3));
     int32_t n_iter = 0, converged = 0;
     double ll_init = 0;
-    check(ctx, lpb200_fit_model(ctx, &m, &p, asLogical(fit_drop), &c, R_NaN, REAL(em), &n_iter, &converged, &ll_init,
-                                REAL(ll), INTEGER(conv)));
+    check(ctx, lpb200_fit_model_from(ctx, &m, &p, asLogical(fit_drop), &c, R_NaN, asInteger(keep_mask), REAL(em), &n_iter,
+                                     &converged, &ll_init, REAL(ll), INTEGER(conv)));
     for (int k = 0; k < c.max_cycles; k++)
         if (ISNAN(REAL(em)[k])) REAL(em)[k] = NA_REAL; /* vecEMLogLikModel <- array(NA, ...) fitModel.R:184 */
     REAL(info)[0] = n_iter;
@@ -275,7 +277,7 @@ static const R_CallMethodDef call_methods[] = {
     {"lp_eval_loglik", (DL_FUNC)&lp_eval_loglik, 4},
     {"lp_fit_mudisp", (DL_FUNC)&lp_fit_mudisp, 4},
     {"lp_fit_pi", (DL_FUNC)&lp_fit_pi, 4},
-    {"lp_fit_model", (DL_FUNC)&lp_fit_model, 5},
+    {"lp_fit_model", (DL_FUNC)&lp_fit_model, 6},
     {"lp_fit_models", (DL_FUNC)&lp_fit_models, 4},
     {"lp_expand_fits", (DL_FUNC)&lp_expand_fits, 6},
     {"lp_lrt", (DL_FUNC)&lp_lrt, 3},

@@ -7,7 +7,7 @@
 #include <Rinternals.h>
 
 SEXP lp_create(SEXP), lp_load_counts_csc(SEXP, SEXP, SEXP, SEXP, SEXP), lp_set_design(SEXP, SEXP);
-SEXP lp_fit_model(SEXP, SEXP, SEXP, SEXP, SEXP), lp_fit_models(SEXP, SEXP, SEXP, SEXP), lp_eval_loglik(SEXP, SEXP, SEXP, SEXP);
+SEXP lp_fit_model(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP), lp_fit_models(SEXP, SEXP, SEXP, SEXP), lp_eval_loglik(SEXP, SEXP, SEXP, SEXP);
 SEXP lp_lrt(SEXP, SEXP, SEXP), lp_fit_pi(SEXP, SEXP, SEXP, SEXP), lp_fit_mudisp(SEXP, SEXP, SEXP, SEXP);
 SEXP lp_expand_fits(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 void fake_r_set_jmp(jmp_buf *);
@@ -82,7 +82,7 @@ int rs_run_impulse_pipeline(int G, int N, const int *cp, const int *ci, const do
     int mA[4] = {0, 0, 1, 0}, mB[4] = {1, 0, 1, 0}, mC[4] = {0, 0, 0, 0}, mD[4] = {1, 0, 0, 0};
     SEXP pA = params_list(G, N, 1, NULL);
     SET_VECTOR_ELT(pA, 4, matrix_of(NULL, N, 1));   /* matDropoutLinModel to be estimated */
-    SEXP rA = lp_fit_model(ctx, ints(mA, 4), pA, int1(1), int1(G));
+    SEXP rA = lp_fit_model(ctx, ints(mA, 4), pA, int1(1), int1(G), int1(0));
     SEXP pAo = VECTOR_ELT(rA, 0);
     memcpy(drop, REAL(list_get(pAo, "matDropoutLinModel")), sizeof(double) * N);
     memcpy(mu_h0, REAL(list_get(pAo, "matMuModel")), sizeof(double) * G);
