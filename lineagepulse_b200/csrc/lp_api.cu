@@ -1266,7 +1266,11 @@ extern "C" int lpb200_fit_mudisp_items(lpb200_ctx *ctx, const lpb200_model *m, l
 template <typename CT>
 static void launch_pi_eval(lpb200_ctx *ctx, const PiArgs &A) {
     dim3 grid((ctx->N + 127) / 128, A.n_chunks);
-    pi_eval_kernel<CT><<<grid, 128, 0, ctx->stream>>>(A);
+    const bool hoist = A.M.drop_model == LPB200_DROP_LOGISTIC && A.D.P == 0;   // gene-independent drop-out rates
+    const int kp = std::max(A.kp, A.shared_nk);
+    if (hoist) pi_eval_kernel<CT, true, 2><<<grid, 128, 0, ctx->stream>>>(A);      // q = 1: at most 2 points per cell
+    else if (kp <= 4) pi_eval_kernel<CT, false, 4><<<grid, 128, 0, ctx->stream>>>(A);
+    else pi_eval_kernel<CT, false, LP_PI_KP><<<grid, 128, 0, ctx->stream>>>(A);
 }
 
 // Tail of the lock-step loop on a SHARDED run.  A cell that needs thousands of BFGS iterations would cost one
@@ -1372,6 +1376,21 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     A.kp = kp;
     A.tail_counts = nullptr;
     A.tail_ld = 0;
+    // (x, phi) part of dnbinom per gene: the gene parameters are fixed for the whole call
+    DevBuf<double> d_xphi;
+    A.xphi_tab = nullptr;
+    A.xphi_w = 0;
+    if (ctx->use_table && lp_disp_is_scalar(ctx->D, M)) {
+        const int w = std::min(ctx->global_max + 1, 1024);
+        if (w > 1) {
+            CK(d_xphi.alloc((size_t)G * w));
+            pi_xphi_table_kernel<<<G, 256, 0, ctx->stream>>>(d_nat.p, lp_n_nat(M), ctx->d_xmax, w, d_xphi.p);
+            CK(cudaGetLastError());
+            ctx->stats.launches++;
+            A.xphi_tab = d_xphi.p;
+            A.xphi_w = w;
+        }
+    }
     A.genes_per_chunk = gpc;
     A.n_chunks = n_chunks;
     A.shared_nk = 0;

@@ -196,6 +196,10 @@ struct PiArgs {
     // tail of a sharded run: the remaining cells' counts over ALL genes (gathered from every shard), cell-major
     const int32_t *tail_counts;   // [n_tail][tail_ld] or nullptr (then the tail reads the resident matrix)
     size_t tail_ld;
+    // (x, phi)-only part of dnbinom per gene, tabulated once per fitPi call when the dispersion is one scalar per gene
+    // (the gene parameters do not change during the call; every round of every cell would recompute it otherwise)
+    const double *xphi_tab;       // [G][xphi_w] or nullptr
+    int xphi_w;
     int genes_per_chunk, n_chunks;
     int shared_nk;          // > 0: ForAllCells, every cell evaluates shared_theta[0..shared_nk)
     double shared_theta[LP_PI_KP * LP_PI_NP];  // optimiser coordinates
@@ -213,7 +217,21 @@ LP_HD void lp_pi_transform(int drop_model, int q, const double *th, double *lin)
 }
 
 #define LP_PI_TILE LP_PI_BLOCK   // genes staged in shared memory per step = one summation block
-template <typename CT>
+
+// tab[g][x] = lp_nb_xphi_part(x, phi_g) for x = 1 .. min(xmax_g, w - 1)
+__global__ void __launch_bounds__(256) pi_xphi_table_kernel(const double *nat, int n_nat, const int32_t *xmax, int w, double *tab) {
+    const int g = blockIdx.x;
+    const double phi = nat[(size_t)g * n_nat];   // nat vector = [disp | ...]
+    const int top = min(xmax[g], w - 1);
+    for (int x = threadIdx.x; x <= top; x += blockDim.x) tab[(size_t)g * w + x] = (x == 0) ? 0.0 : lp_nb_xphi_part((double)x, phi);
+}
+
+// HOIST: gene-independent logistic drop-out model (no matPiConstPredictors, not logistic_ofMu): the rate and
+// log(1 - rate) of each of the cell's points are computed once per cell instead of once per (gene, cell, point) --
+// the same operations on the same operands, hence the same bits.
+// KPMAX: compile-time bound of the points per cell (2q): 2 for the plain logistic model -- the per-point arrays of a
+// 16-point build cost 248 registers per thread (8 warps per SM); 2 / 4 / 16 are instantiated.
+template <typename CT, bool HOIST, int KPMAX>
 __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ PiArgs A) {
     __shared__ PointNat sg[LP_PI_TILE];
     const DevDesign &D = A.D;
@@ -226,15 +244,15 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
 
     // this cell's evaluation points
     int nk = 0;
-    double coef[LP_PI_KP][LP_PI_NP];
+    double coef[KPMAX][LP_PI_NP];
     if (j < D.N) {
         if (A.shared_nk > 0) {
-            nk = A.shared_nk;
+            nk = min(A.shared_nk, KPMAX);   // (the launcher picks KPMAX >= 2q)
             for (int k = 0; k < nk; k++) lp_pi_transform(M.drop_model, q, A.shared_theta + k * LP_PI_NP, coef[k]);
         } else {
             const PiState &st = A.states[j];
             int req = st.req;
-            nk = (req == LP_REQ_F) ? 1 : (req == LP_REQ_GRAD ? 2 * q : 0);
+            nk = min((req == LP_REQ_F) ? 1 : (req == LP_REQ_GRAD ? 2 * q : 0), KPMAX);
             for (int k = 0; k < nk; k++) {
                 double th[LP_PI_NP];
                 for (int i = 0; i < q; i++) th[i] = st.b[i];
@@ -247,15 +265,27 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
         }
     }
     // a block of LP_PI_BLOCK genes is summed in gene order in double; blocks are combined exactly
-    ExactSum ex[LP_PI_KP];
-    double acc[LP_PI_KP];
+    ExactSum ex[KPMAX];
+    double acc[KPMAX];
 #pragma unroll
-    for (int k = 0; k < LP_PI_KP; k++) {
+    for (int k = 0; k < KPMAX; k++) {
         acc[k] = 0.0;
         ex[k].a = ex[k].b = ex[k].bad = 0;
     }
     const double s = (j < D.N && D.sf) ? D.sf[j] : 1.0;
     const CT *base = reinterpret_cast<const CT *>(A.C.ptr);
+    double pi_h[KPMAX], l1m_h[KPMAX];
+    if (HOIST) {
+#pragma unroll
+        for (int k = 0; k < KPMAX; k++) {
+            if (k < nk) {
+                pi_h[k] = lp_dropout_rate(1.0 * coef[k][0]);
+                l1m_h[k] = log(1.0 - pi_h[k]);
+            }
+        }
+    }
+    const double *xtab = A.xphi_tab;
+    const int xw = A.xphi_w;
 
     for (int gt = g0; gt < g1; gt += LP_PI_TILE) {
         __syncthreads();
@@ -276,23 +306,28 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
             double core;  // theta-independent part
             if (x == 0) core = exp(phi * log(phi / (phi + mus)));
             else if (lp_nb_small_x((double)x, phi)) core = lp_dnbinom_small_x((double)x, mus, phi);
-            else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
+            else core = ((xtab && x < xw) ? xtab[(size_t)i * xw + x] : lp_nb_xphi_part((double)x, phi)) + lp_nb_mu_part((double)x, mus, phi);
 #pragma unroll
-            for (int k = 0; k < LP_PI_KP; k++) {
+            for (int k = 0; k < KPMAX; k++) {
                 if (k < nk) {
-                    int u = 1;
-                    double lin = 1.0 * coef[k][0];
-                    if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * coef[k][u++];
-                    for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * coef[k][u];
-                    double pi = lp_dropout_rate(lin);
-                    double v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
+                    double v;
+                    if (HOIST) {
+                        v = (x == 0) ? log((1.0 - pi_h[k]) * core + pi_h[k]) : l1m_h[k] + core;
+                    } else {
+                        int u = 1;
+                        double lin = 1.0 * coef[k][0];
+                        if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * coef[k][u++];
+                        for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * coef[k][u];
+                        double pi = lp_dropout_rate(lin);
+                        v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
+                    }
                     if (v < LP_LL_FLOOR) v = LP_LL_FLOOR;
                     acc[k] += v;
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < LP_PI_KP; k++) {
+        for (int k = 0; k < KPMAX; k++) {
             if (k < nk) {
                 lp_exact_add(ex[k], acc[k]);
                 acc[k] = 0.0;
@@ -302,7 +337,7 @@ __global__ void __launch_bounds__(128) pi_eval_kernel(const __grid_constant__ Pi
     if (j < D.N) {
         const size_t plane = (size_t)A.n_chunks * A.kp * D.N;
 #pragma unroll
-        for (int k = 0; k < LP_PI_KP; k++) {
+        for (int k = 0; k < KPMAX; k++) {
             if (k < nk) {
                 const size_t o = ((size_t)blockIdx.y * A.kp + k) * D.N + j;
                 A.partial_i[o] = ex[k].a;
