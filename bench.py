@@ -532,41 +532,47 @@ def main():
     n_de = 0
     h2d = d2h = 0
     n_e2e = max(1, min(args.steps, 2))
+    e2e_error = None
     if rank == 0:
-        Gt = X_all.shape[0]
-        pinned = torch.empty((Gt, N), dtype=torch.int32).pin_memory()
-        pinned.numpy()[...] = X_all
-        devices = list(range(world)) if world > 1 else None
-        kw = dict(strDropModel="logistic", boolVerbose=False, device=local_rank, devices=devices, **api_kw)
-        if args.warmup > 0:  # one untimed pass of the public API path (first-use allocations of fresh contexts)
-            api.runLineagePulse(pinned.numpy(), annot, **kw)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        e2e_ms = []
-        for _ in range(n_e2e):
-            flush.fill_(1)
-            for dv in range(world):
-                torch.cuda.synchronize(dv)
-            # device-side timing, max over the devices of the call: events on every device's default stream
-            # around the blocking call (its results are on the host when it returns)
-            ev = []
-            for dv in range(world):
-                with torch.cuda.device(dv):
-                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(torch.cuda.default_stream(dv))
-                    ev.append((a, b_))
-            obj = api.runLineagePulse(pinned.numpy(), annot, **kw)
-            n_de = int((obj.dfResults["padj"] < 0.05).sum())
-            for dv in range(world):
-                with torch.cuda.device(dv):
-                    ev[dv][1].record(torch.cuda.default_stream(dv))
-            for dv in range(world):
-                torch.cuda.synchronize(dv)
-            e2e_ms.append(max(a.elapsed_time(b_) for a, b_ in ev))
-        e2e_ms_step = float(np.mean(e2e_ms))
-        e2e_value = Gt / (e2e_ms_step / 1e3)
-        h2d = int(X_all.nbytes + 8 * N * 6 * world)  # counts + pseudotime + 4-column impulse basis + size factors, per device
-        d2h = int(obj.dfResults.shape[0] * 14 * 8 + 8 * Gt * (7 + 1 + 1 + 1) * 2 + 8 * N)  # results table, parameter matrices, drop-out model
-        del flush
+        try:
+            Gt = X_all.shape[0]
+            pinned = torch.empty((Gt, N), dtype=torch.int32).pin_memory()
+            pinned.numpy()[...] = X_all
+            devices = list(range(world)) if world > 1 else None
+            kw = dict(strDropModel="logistic", boolVerbose=False, device=local_rank, devices=devices, **api_kw)
+            if args.warmup > 0:  # one untimed pass of the public API path (first-use allocations of fresh contexts)
+                api.runLineagePulse(pinned.numpy(), annot, **kw)
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            e2e_ms = []
+            for _ in range(n_e2e):
+                flush.fill_(1)
+                for dv in range(world):
+                    torch.cuda.synchronize(dv)
+                # device-side timing, max over the devices of the call: events on every device's default stream
+                # around the blocking call (its results are on the host when it returns)
+                ev = []
+                for dv in range(world):
+                    with torch.cuda.device(dv):
+                        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(torch.cuda.default_stream(dv))
+                        ev.append((a, b_))
+                obj = api.runLineagePulse(pinned.numpy(), annot, **kw)
+                n_de = int((obj.dfResults["padj"] < 0.05).sum())
+                for dv in range(world):
+                    with torch.cuda.device(dv):
+                        ev[dv][1].record(torch.cuda.default_stream(dv))
+                for dv in range(world):
+                    torch.cuda.synchronize(dv)
+                e2e_ms.append(max(a.elapsed_time(b_) for a, b_ in ev))
+            e2e_ms_step = float(np.mean(e2e_ms))
+            e2e_value = Gt / (e2e_ms_step / 1e3)
+            h2d = int(X_all.nbytes + 8 * N * 6 * world)  # counts + pseudotime + 4-column impulse basis + size factors, per device
+            d2h = int(obj.dfResults.shape[0] * 14 * 8 + 8 * Gt * (7 + 1 + 1 + 1) * 2 + 8 * N)  # results table, parameter matrices, drop-out model
+            del flush
+        except Exception as ex:   # the other ranks wait at the host barrier below: report, do not hang them
+            import traceback
+            traceback.print_exc()
+            e2e_error = f"{type(ex).__name__}: {ex}"
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier(group=cpu_group)     # host-side wait (gloo): the other ranks' GPUs stay idle while rank 0 uses them
@@ -635,7 +641,7 @@ def main():
                        "de_genes_q05": n_de},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_step,
+                    "ms_per_step": e2e_ms_step, "error": e2e_error,
                     "api": "lineagepulse_b200.runLineagePulse(host counts" + (f", devices=[0..{world - 1}]): one sharded call" if world > 1 else ")")},
             "gpu_launches": launches,
             "roofline": roofline,
