@@ -1327,6 +1327,8 @@ static int fit_pi_sharded_tail(lpb200_ctx *ctx, const PiArgs &A, const double *d
     T.nat = d_nat_all.p;
     T.tail_counts = d_cols.p;
     T.tail_ld = ld;
+    T.xphi_tab = nullptr;   // the per-gene (x, phi) tables cover this shard's genes only
+    T.xphi_w = 0;
     if (ctx->is_u16) pi_tail_kernel<uint16_t><<<n_tail, 256, 0, ctx->stream>>>(T, d_list);
     else pi_tail_kernel<int32_t><<<n_tail, 256, 0, ctx->stream>>>(T, d_list);
     CK(cudaGetLastError());

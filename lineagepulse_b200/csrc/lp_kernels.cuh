@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
     __shared__ double s_vals[LP_PI_KP];
     __shared__ long long s_ex[LP_PI_KP][3];
     __shared__ double s_coef[LP_PI_KP][LP_PI_NP];
+    __shared__ double s_pi[LP_PI_KP], s_l1m[LP_PI_KP];   // gene-independent logistic model: rate and log(1 - rate) per point
     __shared__ int s_nk;
     const DevDesign &D = A.D;
     const DevModel &M = A.M;
@@ -467,6 +468,9 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
     const CT *base = reinterpret_cast<const CT *>(A.C.ptr);
     // sharded run: D.G, A.nat and D.pi_pred span ALL genes and the cell's counts come from the gathered buffer
     const int32_t *gathered = A.tail_counts ? A.tail_counts + (size_t)blockIdx.x * A.tail_ld : nullptr;
+    const bool hoist = M.drop_model == LPB200_DROP_LOGISTIC && D.P == 0;   // as pi_eval_kernel<.., HOIST = true>: same bits
+    const double *xtab = A.xphi_tab;
+    const int xw = A.xphi_w;
     for (;;) {
         if (tid == 0) {
             int req = st.req;
@@ -479,6 +483,10 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
                     th[c] = bfgs_grad_point(st.b[c], k, A.ndeps);
                 }
                 lp_pi_transform(M.drop_model, q, th, s_coef[k]);
+                if (hoist) {
+                    s_pi[k] = lp_dropout_rate(1.0 * s_coef[k][0]);
+                    s_l1m[k] = log(1.0 - s_pi[k]);
+                }
             }
             s_nk = nk;
         }
@@ -512,16 +520,21 @@ __global__ void __launch_bounds__(256) pi_tail_kernel(const __grid_constant__ Pi
                 double core;
                 if (x == 0) core = exp(phi * log(phi / (phi + mus)));
                 else if (lp_nb_small_x((double)x, phi)) core = lp_dnbinom_small_x((double)x, mus, phi);
-                else core = lp_nb_xphi_part((double)x, phi) + lp_nb_mu_part((double)x, mus, phi);
+                else core = ((xtab && x < xw) ? xtab[(size_t)i * xw + x] : lp_nb_xphi_part((double)x, phi)) + lp_nb_mu_part((double)x, mus, phi);
 #pragma unroll
                 for (int k = 0; k < LP_PI_KP; k++) {
                     if (k < nk) {
-                        int u = 1;
-                        double lin = 1.0 * s_coef[k][0];
-                        if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * s_coef[k][u++];
-                        for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * s_coef[k][u];
-                        double pi = lp_dropout_rate(lin);
-                        double v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
+                        double v;
+                        if (hoist) {
+                            v = (x == 0) ? log((1.0 - s_pi[k]) * core + s_pi[k]) : s_l1m[k] + core;
+                        } else {
+                            int u = 1;
+                            double lin = 1.0 * s_coef[k][0];
+                            if (M.drop_model == LPB200_DROP_LOGISTIC_OFMU) lin += lmu * s_coef[k][u++];
+                            for (int p = 0; p < D.P; p++, u++) lin += D.pi_pred[i + (size_t)p * D.G] * s_coef[k][u];
+                            double pi = lp_dropout_rate(lin);
+                            v = (x == 0) ? log((1.0 - pi) * core + pi) : log(1.0 - pi) + core;
+                        }
                         if (v < LP_LL_FLOOR) v = LP_LL_FLOOR;
                         acc[k] += v;
                     }
