@@ -411,6 +411,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         # a host-side group: ranks that wait while rank 0 drives all GPUs (the e2e leg) must not wait inside an NCCL
         # barrier -- its kernel would spin on the very GPUs rank 0 is using from another process
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # one node: never depend on the container hostname resolving
         cpu_group = dist.new_group(backend="gloo")
     stream = torch.cuda.current_stream()
 
