@@ -604,9 +604,11 @@ def main():
     perm_bytes = 4.0 * G * N               # per-gene cell permutation (non-zero cells first)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
-                # dram__bytes_read + write of the fit kernel is not the bound and is not re-measured per run: see
-                # profiles/README.md (ncu --set full: L2 hit rate 98-99.8 %, DRAM < 0.1 % of peak)
-                "traffic": None,
+                # dram__bytes_read + write of ONE launch (fit B) from the ncu --set full capture at exactly this shape and
+                # count type (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2.csv: 432.4 MB read + 11.7 MB written against
+                # 400 MB of counts + permutation); any other shape: not captured
+                "traffic": 444.1e6 if (G, N, ct_bytes, h1) == (5000, 10000, 4, "impulse") else None,
+                "traffic_source": "ncu --set full of fit B at 5 000 x 10 000 int32 (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2.csv); not re-measured per run",
                 "kernel": f"fit_mudisp_kernel<{ct_name}> (fits B, C, D: three overlapping launches)",
                 "kernel_share_of_step": share,
                 "ole_per_s": (w["B"]["ole"] + w["C"]["ole"] + w["D"]["ole"]) / ker_s,
