@@ -254,16 +254,25 @@ extern "C" lpb200_ctx *lpb200_create(int device) {
         return nullptr;
     }
     // load every fit-kernel variant now: with CUDA's lazy module loading the first launch of a kernel can
-    // wait for running kernels, which would serialise the concurrent fits of lpb200_fit_model_multi
-    for (int ct = 0; ct < 2; ct++)
-        for (int cl = 0; cl < 2; cl++)
-            for (int v = 0; v < LP_N_FIT_VARIANTS; v++) {
-                cudaFuncSetAttribute((const void *)fit_kernel(ct != 0, v, cl != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)fit_smem_bytes(cl != 0));
-                cudaFuncAttributes fa;
-                cudaFuncGetAttributes(&fa, (const void *)fit_kernel(ct != 0, v, cl != 0));   // forces the module load
-            }
-    cudaGetLastError();
+    // wait for running kernels, which would serialise the concurrent fits of lpb200_fit_model_multi.  Once per
+    // device and process: the primary context keeps the modules, later contexts skip the ~20 ms.
+    {
+        static std::mutex loaded_mutex;
+        static std::vector<int> loaded_devices;
+        std::lock_guard<std::mutex> lock(loaded_mutex);
+        if (std::find(loaded_devices.begin(), loaded_devices.end(), device) == loaded_devices.end()) {
+            for (int ct = 0; ct < 2; ct++)
+                for (int cl = 0; cl < 2; cl++)
+                    for (int v = 0; v < LP_N_FIT_VARIANTS; v++) {
+                        cudaFuncSetAttribute((const void *)fit_kernel(ct != 0, v, cl != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)fit_smem_bytes(cl != 0));
+                        cudaFuncAttributes fa;
+                        cudaFuncGetAttributes(&fa, (const void *)fit_kernel(ct != 0, v, cl != 0));   // forces the module load
+                    }
+            cudaGetLastError();
+            loaded_devices.push_back(device);
+        }
+    }
     const char *e = getenv("LPB200_NO_TABLE");
     if (e && atoi(e)) c->use_table = 0;
     e = getenv("LPB200_CTAS_PER_SM");
@@ -387,6 +396,12 @@ extern "C" int lpb200_comm_init(lpb200_ctx *ctx, int rank, int world, const char
         ctx->rank = 0;
         return set_err(ctx, LPB200_E_COMM, "ncclCommInitRank failed: %s", nccl->GetErrorString(r));
     }
+    // NCCL sets a communicator's connections up at its first collective (0.3-1.5 s for 2-8 ranks): do that here, so
+    // that the first all-reduce of a fit is an all-reduce
+    CK(cudaMemsetAsync(ctx->d_xchg + 16, 0, sizeof(double), ctx->stream));
+    r = nccl->AllReduce(ctx->d_xchg + 16, ctx->d_xchg + 16, 1, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) return set_err(ctx, LPB200_E_COMM, "ncclAllReduce (warm-up) failed: %s", nccl->GetErrorString(r));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -20,6 +20,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     std::string error;
 };
@@ -46,11 +48,20 @@ static NcclApi *nccl_api() {
         LP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
         LP_NCCL_SYM(AllReduce, "ncclAllReduce")
         LP_NCCL_SYM(AllGather, "ncclAllGather")
+        LP_NCCL_SYM(GroupStart, "ncclGroupStart")
+        LP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
         LP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef LP_NCCL_SYM
     });
     return api.handle ? &api : nullptr;
 }
+
+// ncclGroupStart / ncclGroupEnd around collectives that one thread issues for several devices
+struct NcclGroup {
+    NcclApi *api;
+    explicit NcclGroup(NcclApi *a) : api(a) { api->GroupStart(); }
+    ~NcclGroup() { api->GroupEnd(); }
+};
 
 // Loopback communicator: several shard contexts on ONE device (lpb200_create_multi with a repeated device id).
 // NCCL cannot put two ranks on one GPU; here the shards' host threads meet at a barrier and every shard adds up

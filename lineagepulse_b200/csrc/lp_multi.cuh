@@ -42,6 +42,26 @@ static CommSet *acquire_comms(const int *devices, int n) {
         delete cs;
         return nullptr;
     }
+    // connection set-up happens at a communicator's first collective: pay it here, once per device list
+    {
+        std::vector<double *> bufs(n, nullptr);
+        bool ok = true;
+        for (int k = 0; k < n && ok; k++)
+            ok = cudaSetDevice(devices[k]) == cudaSuccess && cudaMalloc((void **)&bufs[k], sizeof(double)) == cudaSuccess &&
+                 cudaMemset(bufs[k], 0, sizeof(double)) == cudaSuccess;
+        if (ok) {
+            NcclGroup group(nccl);
+            for (int k = 0; k < n; k++) {
+                cudaSetDevice(devices[k]);
+                nccl->AllReduce(bufs[k], bufs[k], 1, ncclFloat64, ncclSum, cs->comms[k], (cudaStream_t)0);
+            }
+        }
+        for (int k = 0; k < n; k++) {
+            cudaSetDevice(devices[k]);
+            cudaDeviceSynchronize();
+            if (bufs[k]) cudaFree(bufs[k]);
+        }
+    }
     cs->in_use = true;
     g_comm_sets.push_back(cs);
     return cs;
