@@ -542,10 +542,14 @@ def main():
             devices = list(range(world)) if world > 1 else None
             kw = dict(strDropModel="logistic", boolVerbose=False, device=local_rank, devices=devices, **api_kw)
             if args.warmup > 0:  # one untimed pass of the public API path (first-use allocations of fresh contexts)
-                api.runLineagePulse(pinned.numpy(), annot, **kw)
+                api.runLineagePulse(pinned.numpy(), annot, **kw).matCountsProc.engine().close()
             flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
             e2e_ms = []
+            obj = None
             for _ in range(n_e2e):
+                if obj is not None:      # the previous result's GPU context is released outside the timed region
+                    obj.matCountsProc.engine().close()
+                    obj = None
                 flush.fill_(1)
                 for dv in range(world):
                     torch.cuda.synchronize(dv)

@@ -283,6 +283,7 @@ def declare_product_prototypes(lib):
         "lpb200_comm_init": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p]),
         "lpb200_comm_stats": (C.c_int, [vp, P(C.c_uint64), P(C.c_uint64)]),
         "lpb200_destroy": (None, [vp]),
+        "lpb200_release_cached_memory": (C.c_int, [C.c_int]),
         "lpb200_last_error": (C.c_char_p, [vp]),
         "lpb200_set_stream": (C.c_int, [vp, vp]),
         "lpb200_set_collective": (C.c_int, [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]),

@@ -146,7 +146,7 @@ struct PoolBlock {
 static std::vector<PoolBlock> g_pool;
 static size_t g_pool_bytes = 0;
 static std::mutex g_pool_mutex;   // contexts of several host threads share the pool
-static const size_t POOL_CAP_BYTES = (size_t)16 << 30;
+static const size_t POOL_CAP_BYTES = (size_t)32 << 30;   // over all devices of the process
 
 static cudaError_t pool_alloc(void **out, size_t bytes, size_t *got) {
     int dev = 0;
@@ -307,7 +307,8 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    pool_release(c->device);
+    // the scratch pool outlives the context (a caching allocator: the public API makes one context per count matrix,
+    // and a fresh pool would cost every new context some dozens of cudaMalloc); lpb200_release_cached_memory frees it
     free_design(c);
     if (c->d_counts) cudaFree(c->d_counts);
     if (c->d_xmax) cudaFree(c->d_xmax);
@@ -321,6 +322,14 @@ extern "C" void lpb200_destroy(lpb200_ctx *c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
+}
+
+extern "C" int lpb200_release_cached_memory(int device) {
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return LPB200_E_CUDA;
+    pool_release(device);
+    cudaSetDevice(prev);
+    return 0;
 }
 
 extern "C" const char *lpb200_last_error(lpb200_ctx *c) { return c ? c->err.c_str() : "no context (CUDA device unavailable)"; }
