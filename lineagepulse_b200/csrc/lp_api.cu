@@ -1074,6 +1074,17 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
     CK(cudaMemcpyAsync(J.d_theta0.p, J.theta0.data(), sizeof(double) * J.theta0.size(), cudaMemcpyHostToDevice, J.stream));
     CK(cudaMemsetAsync(J.d_queue.p, 0, sizeof(int), J.stream));
     const int threads = fit_threads(N);
+    // specialised kernels for the hot configurations (scalar dispersion, drop-out "none" / fixed "logistic": constant or
+    // impulse mean without confounders -- C1-C3; groups or splines mean with mean batch factors -- C4 / C5), generic otherwise
+    const bool fast_base = !ctx->no_fastpath && lp_disp_is_scalar(D, M) &&
+                           (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
+    const bool fast_ci = fast_base && D.n_conf_mu == 0 && (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE);
+    const bool fast_cov = fast_base && !fast_ci && (M.mu_model == LPB200_MU_GROUPS || M.mu_model == LPB200_MU_SPLINES ||
+                                                    M.mu_model == LPB200_MU_CONSTANT);   // constant: with mean batch factors
+    const bool fast = fast_ci || fast_cov;
+    const int zinb_bit = (M.drop_model == LPB200_DROP_LOGISTIC) ? 1 : 0;
+    const int variant = fast_ci ? (M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) + zinb_bit
+                                : (fast_cov ? (M.mu_model == LPB200_MU_GROUPS ? 5 : (M.mu_model == LPB200_MU_SPLINES ? 7 : 9)) + zinb_bit : 0);
     // CTAs per work item.  A thread-block cluster working on one item divides the duration of an item -- and with it
     // the item-length tail of the dynamic queue -- by the cluster size; the result does not depend on it
     // (virtual-warp summation order, lp_kernels.cuh).  Measured (profiles/README.md): it pays when a launch has few
@@ -1086,24 +1097,13 @@ static int fit_launch(lpb200_ctx *ctx, FitJob &J, const lpb200_control *c) {
         cluster = (N >= 32768 && J.n_items < 8 * slots) ? 2 : 1;
     }
     cluster = std::min(cluster, LP_MAX_CLUSTER);
+    if (fast_cov) cluster = 1;   // the covariate-model kernels are built for one CTA per item only
     if (threads != LP_FIT_THREADS) cluster = 1;
     const bool cl = cluster > 1;
     const size_t smem = fit_smem_bytes(cl);
     // persistent CTAs: as many as stay resident (64 registers per thread; shared memory allows 3 per SM)
     const int smem_limit = (int)((227 * 1024) / (smem + 1024));
     const int per_sm = std::max(1, std::min(ctx->ctas_per_sm * (LP_FIT_THREADS / threads), smem_limit));
-    // specialised kernels for the hot configurations (scalar dispersion, drop-out "none" / fixed "logistic": constant or
-    // impulse mean without confounders -- C1-C3; groups or splines mean with mean batch factors -- C4 / C5), generic otherwise
-    const bool fast_base = !ctx->no_fastpath && lp_disp_is_scalar(D, M) &&
-                           (M.drop_model == LPB200_DROP_NONE || M.drop_model == LPB200_DROP_LOGISTIC);
-    const bool fast_ci = fast_base && D.n_conf_mu == 0 && (M.mu_model == LPB200_MU_CONSTANT || M.mu_model == LPB200_MU_IMPULSE);
-    const bool fast_cov = fast_base && !fast_ci && (M.mu_model == LPB200_MU_GROUPS || M.mu_model == LPB200_MU_SPLINES ||
-                                                    M.mu_model == LPB200_MU_CONSTANT);   // constant: with mean batch factors
-    if (fast_cov) cluster = 1;
-    const bool fast = fast_ci || fast_cov;
-    const int zinb_bit = (M.drop_model == LPB200_DROP_LOGISTIC) ? 1 : 0;
-    const int variant = fast_ci ? (M.mu_model == LPB200_MU_IMPULSE ? 3 : 1) + zinb_bit
-                                : (fast_cov ? (M.mu_model == LPB200_MU_GROUPS ? 5 : (M.mu_model == LPB200_MU_SPLINES ? 7 : 9)) + zinb_bit : 0);
     FitKernelFn kernel = fit_kernel(ctx->is_u16, variant, cl);
     CK(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<size_t>(J.n_items, (size_t)ctx->sm_count * per_sm);
