@@ -1374,7 +1374,8 @@ static int fit_pi_impl(lpb200_ctx *ctx, const DevModel &M, int drop_fit_group, l
     DevBuf<int> d_active, d_conv;
     DevBuf<unsigned> d_evals;
     const int cell_blocks = (N + 127) / 128;
-    int n_chunks = std::max(1, std::min(64, (ctx->sm_count * 4 + cell_blocks - 1) / cell_blocks));
+    // gene chunks: enough CTAs for every SM to hold its 7 resident 128-thread CTAs of the 72-register instantiation
+    int n_chunks = std::max(1, std::min(64, (ctx->sm_count * 8 + cell_blocks - 1) / cell_blocks));
     n_chunks = std::min(n_chunks, G);
     int gpc = (G + n_chunks - 1) / n_chunks;
     gpc = (gpc + LP_PI_BLOCK - 1) / LP_PI_BLOCK * LP_PI_BLOCK;   // chunks start on summation-block boundaries
