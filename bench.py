@@ -511,6 +511,15 @@ def main():
         t_all, g_all = t_local, float(G)
     value = g_all * args.steps / t_all
     ms_per_step = t_all / args.steps * 1e3
+    # per-rank account of the last step: with independent matrices per rank the step is the slowest rank's, and the
+    # lock-step collectives of fit A make every rank wait for the slowest one there too
+    mine = {"step_ms": float(step_ms[-1]), "fit_BCD_ms": float(works[-1]["BCD"]["kernel_ms"]),
+            "fit_A_ms": float(works[-1]["A"]["kernel_ms"])}
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine, group=cpu_group)
+    else:
+        per_rank = [mine]
 
     # ---- timed region 2: end to end through the public API with HOST buffers ("e2e") ----------
     # runLineagePulse(counts, dfAnnotation, ..., devices=[0 .. N-1]) from pinned host memory: ONE call of the
@@ -615,6 +624,7 @@ def main():
                 "traffic_source": "ncu --set full of fit B at 5 000 x 10 000 int32 (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2.csv); not re-measured per run",
                 "kernel": f"fit_mudisp_kernel<{ct_name}> (fits B, C, D: three overlapping launches)",
                 "kernel_share_of_step": share,
+                "kernel_share_of_step_slowest_rank": max(r["fit_BCD_ms"] for r in per_rank) / max(r["step_ms"] for r in per_rank),
                 "ole_per_s": (w["B"]["ole"] + w["C"]["ole"] + w["D"]["ole"]) / ker_s,
                 "flops_per_ole": {"B": flops_per_ole(h1, True, zero_frac, conf_mu or 0), "C": flops_per_ole("constant", False, zero_frac, conf_mu or 0),
                                   "D": flops_per_ole(h1, False, zero_frac, conf_mu or 0)},
@@ -655,6 +665,7 @@ def main():
             "cpu_baseline": cpu,
             "parity": parity,
             "strong": strong,
+            "ranks": {k: [round(r[k], 2) for r in per_rank] for k in ("step_ms", "fit_BCD_ms", "fit_A_ms")},
             "work": {k: {kk: (float(vv) if kk == "kernel_ms" else int(vv)) for kk, vv in v.items()} for k, v in w.items()}}
     print(json.dumps(line), flush=True)
     if world > 1:
