@@ -76,6 +76,16 @@ LP_HD void lp_fast_point(const PointNat &P, FastPoint &F) {
 
 // log-likelihood of observation x (>= 0) of cell j under the lane's point; the per-cell vectors are read only
 // where the term needs them (tt: impulse; pi_ptr: ZINB zero; l1m_ptr: ZINB non-zero)
+// ... given the cell's mean mu (before the size factor)
+template <bool ZINB>
+LP_HD double lp_fast_cell_mu(const FastPoint &F, double mu, int x, int j, const double *sf, const double *pi_ptr,
+                             const double *l1m_ptr, const double *tabp, int tab_len) {
+    const double mus = sf ? mu * sf[j] : mu;
+    if (x == 0) return ZINB ? lp_ll_zero_zinb(mus, F.phi, pi_ptr[j]) : lp_ll_zero_nb(mus, F.phi, F.logphi);
+    const double xd = (double)x;
+    const double xphi = (x < tab_len) ? tabp[x] : lp_nb_xphi_part_cold(xd, F.phi);  // cold: keeps the table code out of the loop body
+    return lp_ll_nonzero(xd, xphi, mus, F.phi, ZINB ? l1m_ptr[j] : 0.0);
+}
 template <int MU, bool ZINB>
 LP_HD double lp_fast_cell(const FastPoint &F, int x, int j, const double *tt, const double *sf, const double *pi_ptr,
                           const double *l1m_ptr, const double *tabp, int tab_len) {
@@ -88,9 +98,5 @@ LP_HD double lp_fast_cell(const FastPoint &F, int x, int j, const double *tt, co
     } else {
         mu = F.p0;
     }
-    const double mus = sf ? mu * sf[j] : mu;
-    if (x == 0) return ZINB ? lp_ll_zero_zinb(mus, F.phi, pi_ptr[j]) : lp_ll_zero_nb(mus, F.phi, F.logphi);
-    const double xd = (double)x;
-    const double xphi = (x < tab_len) ? tabp[x] : lp_nb_xphi_part_cold(xd, F.phi);  // cold: keeps the table code out of the loop body
-    return lp_ll_nonzero(xd, xphi, mus, F.phi, ZINB ? l1m_ptr[j] : 0.0);
+    return lp_fast_cell_mu<ZINB>(F, mu, x, j, sf, pi_ptr, l1m_ptr, tabp, tab_len);
 }

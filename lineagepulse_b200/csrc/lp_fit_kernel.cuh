@@ -167,6 +167,37 @@ struct FastLane {
         const int x = (r < nnz) ? lp_load_count(row, j) : 0;
         return lp_fast_cell<MU, ZINB>(F, x, j, tt, sf, pi_ptr, l1m_ptr, tabp, tab_len);
     }
+    // Gradient request of the impulse model: 16 points = 8 coordinates x (+, -) of one cell in one half warp,
+    // point k moves coordinate k / 2 of (phi, beta1, beta2, h0, h1, h2, t1, t2).  Only k = 2, 3, 12, 13 have a first
+    // sigmoid of their own and only k = 4, 5, 14, 15 a second one; the other values are those of the unmoved
+    // parameters.  Each lane therefore evaluates ONE sigmoid (lane 0 of the half warp the unmoved first one, lane 1
+    // the unmoved second one) and fetches the other by shuffle: 16 instead of 32 exp + reciprocal per cell, the
+    // same operations on the same operands, hence the same bits as term().  Every lane of the warp must call this.
+    static constexpr bool kShareSigmoids = (MU == LP_MU_FAST_IMPULSE);
+    // mean of cell j under the lane's point; shared: the 16-point gradient layout above (every lane of the warp calls)
+    __device__ __forceinline__ double mean(int j, int lane, bool shared) const {
+        if (MU != LP_MU_FAST_IMPULSE) return F.p0;
+        const double t = tt[j];
+        double s1, s2;
+        if (shared) {
+            const int k = lane & 15;
+            const bool own1 = (k == 2) | (k == 3) | (k == 12) | (k == 13), own2 = (k == 4) | (k == 5) | (k == 14) | (k == 15);
+            const bool second = own2 | (k == 1);
+            const double a = (second ? F.b2 : -F.p0) * (t - (second ? F.t2 : F.t1));   // term(): -p0 (t - t1), b2 (t - t2)
+            const double e = lp_exp(a);
+            const double s = (e < 1e300) ? lp_rcp<true>(1.0 + e) : lp_rcp<false>(1.0 + e);
+            const double b1 = __shfl_sync(0xffffffffu, s, lane & 16), b2 = __shfl_sync(0xffffffffu, s, (lane & 16) | 1);
+            s1 = own1 ? s : b1;
+            s2 = own2 ? s : b2;
+        } else {
+            lp_sigmoid_pair(-F.p0 * (t - F.t1), F.b2 * (t - F.t2), s1, s2);
+        }
+        return F.inv_h1 * (F.h0 + (F.h1 - F.h0) * s1) * (F.h2 + (F.h1 - F.h2) * s2);
+    }
+    __device__ __forceinline__ double tail(double mu, int r, int j) const {
+        const int x = (r < nnz) ? lp_load_count(row, j) : 0;
+        return lp_fast_cell_mu<ZINB>(F, mu, x, j, sf, pi_ptr, l1m_ptr, tabp, tab_len);
+    }
 };
 // Group means or a spline mean model, mean batch factors, one scalar dispersion per gene, drop-out "none" or
 // gene-wise fixed (BASELINE configs C4 / C5).  The point stays in shared memory (its group means / spline
@@ -201,6 +232,7 @@ struct CovariateLane {
         int x, g, b0;
     };
     static constexpr bool kDeepPrefetch = true;
+    static constexpr bool kShareSigmoids = false;
     __device__ __forceinline__ Pre preload(int r, int j) const {
         Pre p;
         p.x = (r < nnz) ? lp_load_count(row, j) : 0;
@@ -261,6 +293,7 @@ struct GenericLane {
     }
     struct Pre {};
     static constexpr bool kDeepPrefetch = false;
+    static constexpr bool kShareSigmoids = false;
     __device__ __forceinline__ double term(int r, int j, const Pre &) const {
         const int x = lp_load_count(row, j);
         const double s = A->D.sf ? A->D.sf[j] : 1.0;
@@ -304,7 +337,19 @@ __device__ void lp_eval_points(const FitArgs &A, SH &S, const CT *row, int gene,
     const int stride = LP_VW * cpw;
     for (int v = pwarp; v < LP_VW; v += P) {
         double acc = 0.0;
-        if (active) {
+        if constexpr (LANE::kShareSigmoids) {
+            // one loop for both requests, warp-uniform trip count (the shuffles of the 16-point pass need every lane)
+            const bool shared_pass = (nk == 16);
+            int r = v * cpw + slot;
+            int j = (r < nobs) ? (int)perm[r] : 0;
+            for (int r0 = v * cpw; r0 < nobs; r0 += stride, r += stride) {
+                const int r_next = r + stride;
+                const int j_next = (r_next < nobs) ? (int)perm[r_next] : 0;   // one iteration ahead, as below
+                const double mu = L.mean(j, lane, shared_pass);
+                if (active && r < nobs) acc += L.tail(mu, r, j);
+                j = j_next;
+            }
+        } else if (active) {
             int r = v * cpw + slot;
             int j = (r < nobs) ? (int)perm[r] : 0;
             if constexpr (LANE::kDeepPrefetch) {
