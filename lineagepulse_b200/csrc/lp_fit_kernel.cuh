@@ -94,6 +94,9 @@ struct FitSharedT {
     double red[CL ? 2 : 1][LP_VW][LP_KC + 1];   // [buffer][virtual warp][point]; +1: conflict-free in both directions
     double tab[LP_NTAB][LP_TAB];
     double tab_phi[LP_NTAB];
+    double tab_logphi[LP_NTAB], tab_sphi[LP_NTAB];   // log(phi), stirlerr(phi) of the tables being built
+    double tab0_phi;                              // what tab[0] currently holds: dispersion and length (0: nothing)
+    int tab0_len;
     int tab_of_point[LP_KC];
     int item;
     unsigned epoch;                               // evaluations done (selects the red buffer)
@@ -317,9 +320,21 @@ __device__ void lp_eval_points(const FitArgs &A, SH &S, const CT *row, int gene,
     // (x, phi)-only part of dnbinom tabulated per distinct phi when that is cheaper than N x nk
     const int tab_len = tables_allowed ? lp_table_len(A.use_table, ntabs, xmax, nk, A.D.N) : 0;
     if (tab_len > 0) {
-        for (int e = tid; e < ntabs * tab_len; e += blockDim.x) {
+        // table 0 (the unmoved dispersion) of a gradient request is the table of the function evaluation the line
+        // search accepted just before it: kept when dispersion and length are the same
+        const bool keep0 = (S.tab0_len == tab_len) && (S.tab0_phi == S.tab_phi[0]);
+        if (tid < ntabs) {
+            S.tab_logphi[tid] = lp_log(S.tab_phi[tid]);
+            S.tab_sphi[tid] = lp_stirlerr(S.tab_phi[tid]);
+        }
+        __syncthreads();
+        for (int e = tid + (keep0 ? tab_len : 0); e < ntabs * tab_len; e += blockDim.x) {
             int tsel = e / tab_len, x = e - tsel * tab_len;
-            S.tab[tsel][x] = (x == 0) ? 0.0 : lp_nb_xphi_part((double)x, S.tab_phi[tsel]);
+            S.tab[tsel][x] = (x == 0) ? 0.0 : lp_nb_xphi_part_pre((double)x, S.tab_phi[tsel], S.tab_logphi[tsel], S.tab_sphi[tsel]);
+        }
+        if (tid == 0) {
+            S.tab0_phi = S.tab_phi[0];
+            S.tab0_len = tab_len;
         }
     }
     __syncthreads();
@@ -444,7 +459,10 @@ fit_mudisp_kernel(const __grid_constant__ FitArgs A) {
     const int n = M.n_theta;
     const bool scalar_phi = lp_disp_is_scalar(D, M);
     const unsigned crank = CL ? lp_cluster_ctarank() : 0u;
-    if (tid == 0) S.epoch = 0;
+    if (tid == 0) {
+        S.epoch = 0;
+        S.tab0_len = 0;
+    }
 
     for (;;) {
         if (tid == 0 && crank == 0) S.item = atomicAdd(A.queue, 1);

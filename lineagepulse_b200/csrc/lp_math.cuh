@@ -153,12 +153,15 @@ LP_HD bool lp_div_safe(double mu, double phi) { return mu > 1e-100 && mu < 1e100
 // Part of dnbinom_mu that depends on (x, phi) only; tabulated per evaluation point when phi is
 // one scalar per gene.  n = x + phi and xm = n - phi are formed as R forms them (so the loss of
 // digits of n - phi at huge phi is reproduced).
-LP_HD double lp_nb_xphi_part(double x, double phi) {
+// The two pieces that do not depend on x are arguments (logphi = lp_log(phi), sphi = lp_stirlerr(phi)): a table
+// over x forms them once.
+LP_HD double lp_nb_xphi_part_pre(double x, double phi, double logphi, double sphi) {
     double n = x + phi;
     double xm = n - phi;
-    double lf = LP_LN_2PI + lp_log(phi) + lp_log1p(-phi / n);
-    return lp_log(phi / (phi + x)) + (lp_stirlerr(n) - lp_stirlerr(phi) - lp_stirlerr(xm)) - 0.5 * lf;
+    double lf = LP_LN_2PI + logphi + lp_log1p(-phi / n);
+    return lp_log(phi / (phi + x)) + (lp_stirlerr(n) - sphi - lp_stirlerr(xm)) - 0.5 * lf;
 }
+LP_HD double lp_nb_xphi_part(double x, double phi) { return lp_nb_xphi_part_pre(x, phi, lp_log(phi), lp_stirlerr(phi)); }
 
 // Part that depends on mu: -bd0(phi, n p) - bd0(n - phi, n q)
 template <bool FAST>
