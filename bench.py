@@ -618,10 +618,10 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 # dram__bytes_read + write of ONE launch (fit B) from the ncu --set full capture at exactly this shape and
-                # count type (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2.csv: 432.4 MB read + 11.7 MB written against
+                # count type (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2_final.csv: 433.6 MB read + 22.1 MB written against
                 # 400 MB of counts + permutation); any other shape: not captured
-                "traffic": 444.1e6 if (G, N, ct_bytes, h1) == (5000, 10000, 4, "impulse") else None,
-                "traffic_source": "ncu --set full of fit B at 5 000 x 10 000 int32 (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2.csv); not re-measured per run",
+                "traffic": 455.7e6 if (G, N, ct_bytes, h1) == (5000, 10000, 4, "impulse") else None,
+                "traffic_source": "ncu --set full of fit B at 5 000 x 10 000 int32 (profiles/ncu_fit_mudisp_impulse_zinb_c2_r2_final.csv); not re-measured per run",
                 "kernel": f"fit_mudisp_kernel<{ct_name}> (fits B, C, D: three overlapping launches)",
                 "kernel_share_of_step": share,
                 "kernel_share_of_step_slowest_rank": max(r["fit_BCD_ms"] for r in per_rank) / max(r["step_ms"] for r in per_rank),
