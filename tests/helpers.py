@@ -106,3 +106,28 @@ def best_start(ll_items, n_starts):
     ll = np.asarray(ll_items).reshape(-1, n_starts)
     best = np.argmax(ll, axis=1)   # first maximum
     return best, ll[np.arange(len(ll)), best]
+
+
+def edge_datasets():
+    """Degenerate and ragged shapes for the fit path: one gene x five cells, a gene with a single non-zero
+    observation, gene / cell counts that are not multiples of the 16-gene summation blocks, the 32-lane warps or
+    the 64-element row pitch, counts beyond the (x, phi) table (1 024 entries) and beyond uint16 (int32 storage),
+    NA observations (-1) and size factors.  Yields (tag, dataset)."""
+    rng = np.random.default_rng(7)
+    for G, N, single, big, na, sf in ((1, 5, False, False, False, False), (1, 7, True, False, False, False),
+                                      (3, 33, False, False, True, True), (17, 97, False, True, False, False),
+                                      (2, 64, False, True, True, True), (5, 1025, False, False, False, False)):
+        t = np.linspace(0, 1, N)
+        mu = rng.uniform(0.5, 60, (G, 1)) * (1 + 0.5 * np.sin(3 * t)[None, :])
+        X = rng.negative_binomial(3, 3 / (3 + mu)).astype(np.int32)
+        X[rng.uniform(size=X.shape) < 0.1] = 0
+        if single:
+            X[0, :] = 0
+            X[0, N // 2] = 7
+        if big:
+            X[-1, 0] = 70000
+            X[-1, 1] = 1500
+        if na:
+            X[0, 1] = -1
+            X[G - 1, N - 1] = -1
+        yield f"{G}x{N}", {"X": X, "t": t, "G": G, "N": N, "sf": rng.uniform(0.6, 1.5, N) if sf else None}

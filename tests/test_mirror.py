@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from lineagepulse_b200 import _cabi as A
-from tests.helpers import GOLDEN, best_start, design_for, model, rel, theta0_items
+from tests.helpers import GOLDEN, best_start, design_for, edge_datasets, model, rel, theta0_items
 from tests.mirror_harness import Mirror, rcp64h_table
 
 
@@ -120,3 +120,34 @@ def test_mirror_vs_oracle_is_arithmetic_mode_only(mir, oracle, c1):
         # what is not chaotic: every start ends with optim's code 0 / 1, and the total log-likelihood agrees
         assert np.all(np.isin(mr["conv_items"], (0, 1)))
         assert abs(ll_m.sum() - ll_ld.sum()) <= 1e-4 * abs(ll_ld.sum())
+
+
+def test_mirror_on_degenerate_and_ragged_shapes(mir, oracle):
+    """One gene x five cells, a single non-zero observation, shapes off every block / warp / pitch multiple, counts
+    beyond the (x, phi) table and beyond uint16, NA observations with size factors (tests.helpers.edge_datasets):
+    constant fits land on the oracle's optimum, every impulse start ends with optim's code 0 / 1 and a finite
+    log-likelihood not below the constant model's by more than the optimiser's tolerance.  The GPU test
+    test_edge_shapes_kernel_equals_mirror_bitwise runs the same inputs through the kernel."""
+    n_cases = 0
+    for tag, ds in edge_datasets():
+        d = design_for(ds)
+        for drop in ("none", "logistic"):
+            ll = {}
+            for mu in ("constant", "impulse"):
+                m = model(mu, drop=drop)
+                p0 = oracle.init_params(ds["X"], d, m)
+                if drop != "none":
+                    p0.mat_drop[:, 0] = -2.0
+                th0, ns = theta0_items(oracle, ds["X"], d, m, p0)
+                mr = mir.fit_items(d, m, ds["X"], th0, ns, drop=p0.mat_drop)
+                assert np.all(np.isin(mr["conv_items"], (0, 1))) and np.isfinite(mr["ll_items"]).all(), (tag, mu, drop)
+                _, ll[mu] = best_start(mr["ll_items"], ns)
+                if mu == "constant":
+                    po = p0.copy()
+                    ro = oracle.fit_mudisp(ds["X"], d, m, po)
+                    assert np.array_equal(mr["conv_items"], ro["conv"]), (tag, drop)
+                    assert rel(ll[mu], ro["ll"]).max() < 1e-10, (tag, drop)
+                n_cases += 1
+            # the impulse model contains the constant one (h0 = h1 = h2): its best start cannot be worse
+            assert np.all(ll["impulse"] >= ll["constant"] - 1e-6 * np.abs(ll["constant"])), (tag, drop)
+    assert n_cases == 24
