@@ -208,3 +208,32 @@ def test_test_dropout_table():
             assert abs(row["p"] - chi2.sf(row["deviance"], extra)) <= 1e-12 * chi2.sf(row["deviance"], extra) + 1e-300
         else:
             assert row["p"] == 0.0   # pchisq(q > 0, df = 0, lower.tail = FALSE)
+
+
+def test_bench_contract_without_a_gpu():
+    """bench.py's two arms on a box without a GPU: the reference arm (the CPU oracle pipeline on the host cores) prints
+    ONE JSON line with the contract's keys -- the driver computes the GPU / CPU ratio from it -- and the native arm
+    refuses to run instead of falling back to the CPU."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU for the native-arm half")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    common = ["--steps", "2", "--warmup", "1", "--genes", "64", "--cells", "300"]
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--cpu-budget-s", "3"] + common, cwd=root,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "genes/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = subprocess.run([sys.executable, "bench.py", "--no-cpu-baseline", "--no-strong"] + common, cwd=root,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+    assert not any(ln.startswith("{") for ln in r.stdout.splitlines())
