@@ -237,3 +237,47 @@ def test_bench_contract_without_a_gpu():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
     assert not any(ln.startswith("{") for ln in r.stdout.splitlines())
+
+
+def test_r_wrappers_static_checks():
+    """R cannot parse r_shim/R/lpb200_wrappers.R here (no R in the image); a lexer (tests/r_lint.py) checks what a
+    never-run wrapper gets wrong: strings terminate and brackets nest; every .Call names a routine of the shim's
+    registration table with that table's argument count, which is also the C function's; every list element the C
+    side looks up by name is set somewhere on the R side; the wrappers keep the reference's function signatures
+    (R/srcLineagePulse_fitMeanDispersion.R:853-859, fitDropout.R:418-422, evalLogLik.R:307-313, fitModel.R:137-158)."""
+    from tests import r_lint
+    wr = open(os.path.join(ROOT, "r_shim", "R", "lpb200_wrappers.R")).read()
+    csrc = open(os.path.join(ROOT, "r_shim", "lp_rshim.c")).read()
+    toks = r_lint.check_nesting(wr)
+    table = {m.group(1): int(m.group(3)) for m in re.finditer(r'\{"(lp_\w+)",\s*\(DL_FUNC\)&(\w+),\s*(\d+)\}', csrc)}
+    assert len(table) >= 11
+    for name, arity in table.items():   # the C definitions take as many SEXPs as the table says
+        m = re.search(r"^SEXP\s+" + name + r"\s*\(([^)]*)\)", csrc, re.M)
+        assert m, name
+        assert m.group(1).count("SEXP") == arity, (name, m.group(1), arity)
+    called = set()
+    for line, args in r_lint.calls(toks, ".Call"):
+        assert args and args[0][0][0] == "str", f"line {line}: .Call without a routine name"
+        routine = args[0][0][1]
+        assert routine in table, f"line {line}: .Call of unregistered routine {routine}"
+        assert len(args) - 1 == table[routine], f"line {line}: {routine} takes {table[routine]} arguments, {len(args) - 1} given"
+        called.add(routine)
+    assert {"lp_create", "lp_load_counts_csc", "lp_load_counts_dense", "lp_set_design", "lp_eval_loglik", "lp_fit_mudisp",
+            "lp_fit_pi", "lp_fit_model", "lp_fit_models", "lp_lrt"} <= called
+    # names the shim reads from R lists are names the R side writes (as list(... name = ...) or x$name <- / x[["name"]] <-)
+    r_names = {t[1] for t in toks if t[0] in ("name", "str")}
+    for name in set(re.findall(r'list_get\(\w+,\s*"(\w+)"\)', csrc)):
+        assert name in r_names, f"the shim looks up list element {name!r} which the R wrappers never mention"
+    # reference signatures (argument names in order; the wrappers may append optional arguments)
+    defs = r_lint.function_defs(toks)
+    ref = {"fitMuDisp": ["matCountsProc", "vecNormConst", "lsMuModel", "lsDispModel", "lsDropModel", "matWeights"],
+           "fitPi": ["matCounts", "lsMuModel", "lsDispModel", "lsDropModel"],
+           "evalLogLikMatrix": ["matCounts", "lsMuModel", "lsDispModel", "lsDropModel", "matWeights", "boolConstModelOnMMLL"]}
+    for fn, formals in ref.items():
+        assert defs[fn][: len(formals)] == formals, (fn, defs[fn])
+    for fn in ("fitModel", "fitLPModels", "fitModelsConcurrently", "lpAttachCounts"):
+        assert fn in defs
+    # the lexer itself rejects the defects it is there for
+    for bad in ('f <- function(x) { g(x[[1]) }', 'x <- "abc', 'f(a, b))'):
+        with pytest.raises(SyntaxError):
+            r_lint.check_nesting(bad)
