@@ -215,6 +215,28 @@ def _params_from_models(design, model, lsMuModel, lsDispModel, lsDropModel) -> A
     return p
 
 
+def _control_from_models(lsMuModel=None, lsDropModel=None, control=None) -> A.Control:
+    """The optimiser constants of a boundary call.  The reference reads them from the model lists --
+    lsMuModelGlobal$MAXIT_BFGS_MuDisp / RELTOL_BFGS_MuDisp (fitMeanDispersion.R:912-913) and
+    lsDropModelGlobal$MAXIT_BFGS_Pi / RELTOL_BFGS_Pi (fitDropout.R:291-292, :364-365) -- where fitModel put its
+    constants (fitModel.R:164-175); a list without them (hand-built models) gets those constants.  An explicit
+    ``control`` wins (testing)."""
+    if control is not None:
+        return control
+    ctl = A.default_control()
+    gm = (lsMuModel or {}).get("lsMuModelGlobal") or {}
+    gp = (lsDropModel or {}).get("lsDropModelGlobal") or {}
+    if gm.get("MAXIT_BFGS_MuDisp") is not None:
+        ctl.maxit_mudisp = int(gm["MAXIT_BFGS_MuDisp"])
+    if gm.get("RELTOL_BFGS_MuDisp") is not None:
+        ctl.reltol_mudisp = float(gm["RELTOL_BFGS_MuDisp"])
+    if gp.get("MAXIT_BFGS_Pi") is not None:
+        ctl.maxit_pi = int(gp["MAXIT_BFGS_Pi"])
+    if gp.get("RELTOL_BFGS_Pi") is not None:
+        ctl.reltol_pi = float(gp["RELTOL_BFGS_Pi"])
+    return ctl
+
+
 # ---------------------------------------------------------------------------------------------
 # L2 boundary functions
 # ---------------------------------------------------------------------------------------------
@@ -236,7 +258,7 @@ def fitMuDisp(matCountsProc, vecNormConst=None, lsMuModel=None, lsDispModel=None
     reference (size factors travel inside lsMuModelGlobal, initialiseMuModel.R:73)."""
     counts, eng, design, model = _prepare(matCountsProc, lsMuModel, lsDispModel, lsDropModel)
     p = _params_from_models(design, model, lsMuModel, lsDispModel, lsDropModel)
-    r = eng.fit_mudisp(model, p, control)
+    r = eng.fit_mudisp(model, p, _control_from_models(lsMuModel, lsDropModel, control))
     return {"matMuModel": p.mat_mu, "lsmatBatchModelMu": p.batch_mu or None, "matDispModel": p.mat_disp,
             "lsmatBatchModelDisp": p.batch_disp or None, "vecConvergence": r["conv"], "vecLL": r["ll"]}
 
@@ -247,7 +269,7 @@ def fitPi(matCounts, lsMuModel, lsDispModel, lsDropModel, control=None):
     if model.drop_model == A.DROP_NONE:
         raise LineagePulseError("ERROR fitZINBPi: lsDropModel$lsDropModelGlobal$strDropModel=none not recognised.")
     p = _params_from_models(design, model, lsMuModel, lsDispModel, lsDropModel)
-    r = eng.fit_pi(model, p, control)
+    r = eng.fit_pi(model, p, _control_from_models(lsMuModel, lsDropModel, control))
     return {"matDropoutLinModel": p.mat_drop, "vecConverged": r["conv"], "vecLL": r["ll"]}
 
 

@@ -93,6 +93,16 @@ lpParams <- function(lsMuModel, lsDispModel, lsDropModel) {
          matDropoutLinModel = if (is.null(lsDropModel$matDropoutLinModel)) NULL else lsDropModel$matDropoutLinModel + 0)
 }
 
+## optimiser constants of the next fit: the reference reads them from the model lists (fitMeanDispersion.R:912-913,
+## fitDropout.R:291-292) and from fitModel's scaMaxEstimationCycles (fitModel.R:156); absent entries -> NA -> the
+## constants of fitModel.R:164-175
+lpControl <- function(lsMuModel, lsDropModel, scaMaxEstimationCycles = NA) {
+    pick <- function(x) if (is.null(x)) NA_real_ else as.double(x)
+    gm <- lsMuModel$lsMuModelGlobal; gp <- lsDropModel$lsDropModelGlobal
+    invisible(.Call("lp_set_control", c(pick(gm$MAXIT_BFGS_MuDisp), pick(gm$RELTOL_BFGS_MuDisp), pick(gp$MAXIT_BFGS_Pi),
+                                        pick(gp$RELTOL_BFGS_Pi), as.double(scaMaxEstimationCycles))))
+}
+
 lpSplitBatch <- function(mat, vecNBatches) {
     if (is.null(mat)) return(NULL)
     ends <- cumsum(vecNBatches); starts <- ends - vecNBatches + 1
@@ -112,6 +122,7 @@ fitMuDisp <- function(matCountsProc, vecNormConst, lsMuModel, lsDispModel, lsDro
     if (lsMuModel$lsMuModelGlobal$strMuModel == "MM")
         stop("LineagePulse ERROR: fitMMZINB() not yet supported. Contact developer.")
     ctx <- lpSetDesign(lpContext(matCountsProc), lpDesign(matCountsProc, lsMuModel, lsDispModel, lsDropModel))
+    lpControl(lsMuModel, lsDropModel)
     res <- .Call("lp_fit_mudisp", ctx, lpModel(lsMuModel, lsDispModel, lsDropModel),
                  lpParams(lsMuModel, lsDispModel, lsDropModel), nrow(matCountsProc))
     p <- res[[1]]
@@ -126,6 +137,7 @@ fitMuDisp <- function(matCountsProc, vecNormConst, lsMuModel, lsDispModel, lsDro
 fitPi <- function(matCounts, lsMuModel, lsDispModel, lsDropModel) {
     ctx <- lpSetDesign(lpContext(matCounts), lpDesign(matCounts, lsMuModel, lsDispModel, lsDropModel))
     nOut <- if (lsDropModel$lsDropModelGlobal$strDropFitGroup == "PerCell") ncol(matCounts) else 1L
+    lpControl(lsMuModel, lsDropModel)
     res <- .Call("lp_fit_pi", ctx, lpModel(lsMuModel, lsDispModel, lsDropModel),
                  lpParams(lsMuModel, lsDispModel, lsDropModel), nOut)
     matDropoutLinModel <- res[[1]]$matDropoutLinModel
@@ -166,8 +178,10 @@ fitModel <- function(matCounts, dfAnnotation, vecConfoundersMu = NULL, vecConfou
                                      strDropFitGroup = strDropFitGroup, MAXIT_BFGS_Pi = 10000, RELTOL_BFGS_Pi = 10^(-8))
     ctx <- lpSetDesign(lpContext(matCounts), lpDesign(matCounts, lsMuModel, lsDispModel, lsDropModel))
     ## warm-start hooks (fitModel.R:147-151): which of the matrices are the caller's initial values
-    scaKeepMask <- 1L * !is.null(matMuModelInit) + 2L * !is.null(lsmatBatchModelInitMu) +
-        4L * !is.null(matDispModelInit) + 8L * !is.null(lsmatBatchModelInitDisp)
+    ## (unary ! binds more loosely than * and + in R: the parentheses are needed)
+    scaKeepMask <- 1L * (!is.null(matMuModelInit)) + 2L * (!is.null(lsmatBatchModelInitMu)) +
+        4L * (!is.null(matDispModelInit)) + 8L * (!is.null(lsmatBatchModelInitDisp))
+    lpControl(lsMuModel, lsDropModel, scaMaxEstimationCycles)
     res <- .Call("lp_fit_model", ctx, lpModel(lsMuModel, lsDispModel, lsDropModel),
                  lpParams(lsMuModel, lsDispModel, lsDropModel), boolFitDrop, nrow(matCounts), as.integer(scaKeepMask))
     p <- res[[1]]; info <- res[[5]]
@@ -215,6 +229,7 @@ fitModelsConcurrently <- function(matCounts, dfAnnotation, lsSpecs, vecConfounde
     ctx <- lpSetDesign(lpContext(matCounts), lpDesign(matCounts, lsInit[[idxFull]]$lsMuModel, lsInit[[idxFull]]$lsDispModel,
                                                       lsSpecs[[1]]$lsDropModel))
     matModels <- vapply(lsInit, function(m) lpModel(m$lsMuModel, m$lsDispModel, m$lsDropModel), integer(4))
+    lpControl(lsInit[[idxFull]]$lsMuModel, lsSpecs[[1]]$lsDropModel)
     res <- .Call("lp_fit_models", ctx, matModels,
                  lapply(lsInit, function(m) lpParams(m$lsMuModel, m$lsDispModel, m$lsDropModel)), nrow(matCounts))
     G <- nrow(matCounts)

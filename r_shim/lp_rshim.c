@@ -45,6 +45,41 @@ static void check(lpb200_ctx *ctx, int rc) { /* any optimiser error aborts, as f
     if (rc != 0) error("LineagePulse (lpb200, code %d): %s", rc, lpb200_last_error(ctx));
 }
 
+/* ---- optimiser constants --------------------------------------------------------------------
+ * The reference keeps them in the model lists (lsMuModelGlobal$MAXIT_BFGS_MuDisp / RELTOL_BFGS_MuDisp,
+ * fitMeanDispersion.R:912-913; lsDropModelGlobal$MAXIT_BFGS_Pi / RELTOL_BFGS_Pi, fitDropout.R:291-292) and
+ * fitModel's scaMaxEstimationCycles (fitModel.R:156,243).  The R wrappers send them before a fit with
+ * .Call("lp_set_control", c(maxit_mudisp, reltol_mudisp, maxit_pi, reltol_pi, max_cycles)); NA entries and a
+ * shorter vector leave fitModel.R:164-175's constants.  R calls .Call from one thread: a static is enough. */
+static lpb200_control g_control;
+static int g_control_set = 0;
+static const lpb200_control *current_control(void) {
+    if (!g_control_set) {
+        lpb200_default_control(&g_control);
+        g_control_set = 1;
+    }
+    return &g_control;
+}
+SEXP lp_set_control(SEXP v) {
+    lpb200_default_control(&g_control);
+    g_control_set = 1;
+    if (v != R_NilValue) {
+        int n = LENGTH(v);
+        const double *x = REAL(v);
+        if (n > 0 && !ISNAN(x[0])) g_control.maxit_mudisp = (int)x[0];
+        if (n > 1 && !ISNAN(x[1])) g_control.reltol_mudisp = x[1];
+        if (n > 2 && !ISNAN(x[2])) g_control.maxit_pi = (int)x[2];
+        if (n > 3 && !ISNAN(x[3])) g_control.reltol_pi = x[3];
+        if (n > 4 && !ISNAN(x[4])) g_control.max_cycles = (int)x[4];
+        if (g_control.maxit_mudisp < 0 || g_control.maxit_pi < 0 || g_control.max_cycles < 1 ||
+            !(g_control.reltol_mudisp >= 0) || !(g_control.reltol_pi >= 0)) {
+            lpb200_default_control(&g_control);
+            error("LineagePulse: lp_set_control: bad optimiser constants");
+        }
+    }
+    return R_NilValue;
+}
+
 /* ---- context + data ------------------------------------------------------------------------- */
 /* .Call("lp_create", devices) -> external pointer with finalizer.  devices: integer vector of CUDA device ids;
  * one id = one GPU, several = one gene-sharded context over all of them (lpb200_create_multi): what scaNProc /
@@ -151,8 +186,7 @@ SEXP lp_fit_mudisp(SEXP sctx, SEXP model, SEXP params, SEXP n_genes) {
     lpb200_ctx *ctx = ctx_of(sctx);
     lpb200_model m = model_of(model);
     lpb200_params p = params_of(params);
-    lpb200_control c;
-    lpb200_default_control(&c);
+    lpb200_control c = *current_control();
     int G = asInteger(n_genes);
     SEXP ll = PROTECT(allocVector(REALSXP, G)), conv = PROTECT(allocVector(INTSXP, G));
     check(ctx, lpb200_fit_mudisp(ctx, &m, &p, &c, REAL(ll), INTEGER(conv)));
@@ -169,8 +203,7 @@ SEXP lp_fit_pi(SEXP sctx, SEXP model, SEXP params, SEXP n_out) {
     lpb200_ctx *ctx = ctx_of(sctx);
     lpb200_model m = model_of(model);
     lpb200_params p = params_of(params);
-    lpb200_control c;
-    lpb200_default_control(&c);
+    lpb200_control c = *current_control();
     int n = asInteger(n_out);
     SEXP ll = PROTECT(allocVector(REALSXP, n)), conv = PROTECT(allocVector(INTSXP, n));
     check(ctx, lpb200_fit_pi(ctx, &m, &p, &c, REAL(ll), INTEGER(conv)));
@@ -189,8 +222,7 @@ SEXP lp_fit_model(SEXP sctx, SEXP model, SEXP params, SEXP fit_drop, SEXP n_gene
     lpb200_ctx *ctx = ctx_of(sctx);
     lpb200_model m = model_of(model);
     lpb200_params p = params_of(params);
-    lpb200_control c;
-    lpb200_default_control(&c);
+    lpb200_control c = *current_control();
     int G = asInteger(n_genes);
     SEXP em = PROTECT(allocVector(REALSXP, c.max_cycles)), ll = PROTECT(allocVector(REALSXP, G));
     SEXP conv = PROTECT(allocVector(INTSXP, G)), info = PROTECT(allocVector(REALSXP, 3));
@@ -227,8 +259,7 @@ SEXP lp_fit_models(SEXP sctx, SEXP models, SEXP params, SEXP n_genes) {
         m[j].drop_fit_group = INTEGER(models)[4 * j + 3];
         p[j] = params_of(VECTOR_ELT(params, j));
     }
-    lpb200_control c;
-    lpb200_default_control(&c);
+    lpb200_control c = *current_control();
     SEXP ll_init = PROTECT(allocVector(REALSXP, n_jobs)), em = PROTECT(allocVector(REALSXP, n_jobs));
     SEXP convd = PROTECT(allocVector(INTSXP, n_jobs)), ll = PROTECT(allocVector(REALSXP, (long)n_jobs * G));
     SEXP conv = PROTECT(allocVector(INTSXP, (long)n_jobs * G));
@@ -270,6 +301,7 @@ SEXP lp_lrt(SEXP ll_full, SEXP ll_red, SEXP ddf) {
 }
 
 static const R_CallMethodDef call_methods[] = {
+    {"lp_set_control", (DL_FUNC)&lp_set_control, 1},
     {"lp_create", (DL_FUNC)&lp_create, 1},
     {"lp_load_counts_csc", (DL_FUNC)&lp_load_counts_csc, 5},
     {"lp_load_counts_dense", (DL_FUNC)&lp_load_counts_dense, 2},

@@ -9,7 +9,7 @@
 SEXP lp_create(SEXP), lp_load_counts_csc(SEXP, SEXP, SEXP, SEXP, SEXP), lp_set_design(SEXP, SEXP);
 SEXP lp_fit_model(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP), lp_fit_models(SEXP, SEXP, SEXP, SEXP), lp_eval_loglik(SEXP, SEXP, SEXP, SEXP);
 SEXP lp_lrt(SEXP, SEXP, SEXP), lp_fit_pi(SEXP, SEXP, SEXP, SEXP), lp_fit_mudisp(SEXP, SEXP, SEXP, SEXP);
-SEXP lp_expand_fits(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+SEXP lp_expand_fits(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP), lp_set_control(SEXP);
 void fake_r_set_jmp(jmp_buf *);
 const char *fake_r_last_error(void);
 void fake_r_finalize(SEXP);
@@ -130,4 +130,34 @@ int rs_released_context_raises(char *errbuf) {
     lp_eval_loglik(ctx, ints(m, 4), params_list(4, 4, 1, NULL), int1(4));
     fake_r_set_jmp(NULL);
     return 0;
+}
+
+/* lp_set_control: NULL and NA entries keep fitModel.R:164-175's constants, values are taken, nonsense raises an R error
+ * and leaves the defaults.  Returns 0 when all of that holds (no GPU needed). */
+int rs_set_control_checks(char *errbuf) {
+    jmp_buf jb;
+    fake_r_set_jmp(&jb);
+    if (setjmp(jb)) {
+        strncpy(errbuf, fake_r_last_error(), 511);
+        fake_r_set_jmp(NULL);
+        return 100;
+    }
+    lp_set_control(R_NilValue);
+    double ok[5] = {500, 1e-6, R_NaReal, R_NaReal, 5};
+    lp_set_control(reals(ok, 5));
+    double shorter[2] = {R_NaReal, 1e-7};
+    lp_set_control(reals(shorter, 2));
+    fake_r_set_jmp(NULL);
+    jmp_buf jb2;
+    fake_r_set_jmp(&jb2);
+    if (setjmp(jb2)) {
+        strncpy(errbuf, fake_r_last_error(), 511);
+        fake_r_set_jmp(NULL);
+        lp_set_control(R_NilValue);
+        return 0;   /* the bad vector raised */
+    }
+    double bad[5] = {1000, -1.0, 10000, 1e-8, 0};
+    lp_set_control(reals(bad, 5));
+    fake_r_set_jmp(NULL);
+    return 1;       /* no error: wrong */
 }

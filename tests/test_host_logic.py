@@ -181,6 +181,9 @@ def test_r_shim_compiles_and_links():
                "fitModel <- function", "fitLPModels <- function", "fitModelsConcurrently <- function"):
         assert fn in wr
     assert wr.count("(") == wr.count(")") and wr.count("{") == wr.count("}")   # R cannot parse it here; at least balanced
+    err = C.create_string_buffer(512)
+    assert lib.rs_set_control_checks(err) == 0, err.value
+    assert b"bad optimiser constants" in err.value
     import torch
     if not torch.cuda.is_available():
         err = C.create_string_buffer(512)
@@ -262,7 +265,10 @@ def test_r_wrappers_static_checks():
         assert routine in table, f"line {line}: .Call of unregistered routine {routine}"
         assert len(args) - 1 == table[routine], f"line {line}: {routine} takes {table[routine]} arguments, {len(args) - 1} given"
         called.add(routine)
-    assert {"lp_create", "lp_load_counts_csc", "lp_load_counts_dense", "lp_set_design", "lp_eval_loglik", "lp_fit_mudisp",
+    # R's unary ! binds more loosely than arithmetic: `2L * !a + 4L * !b` is 2L * !(a + 4L * !b)
+    for (k0, t0), (k1, t1) in zip([t[:2] for t in toks], [t[:2] for t in toks[1:]]):
+        assert not (k0 == "op" and t0 in ("*", "+", "-", "/", "^") and (k1, t1) == ("op", "!")), "unparenthesised ! after " + t0
+    assert {"lp_set_control", "lp_create", "lp_load_counts_csc", "lp_load_counts_dense", "lp_set_design", "lp_eval_loglik", "lp_fit_mudisp",
             "lp_fit_pi", "lp_fit_model", "lp_fit_models", "lp_lrt"} <= called
     # names the shim reads from R lists are names the R side writes (as list(... name = ...) or x$name <- / x[["name"]] <-)
     r_names = {t[1] for t in toks if t[0] in ("name", "str")}
