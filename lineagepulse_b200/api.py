@@ -379,6 +379,10 @@ def fitModel(matCounts, dfAnnotation, vecConfoundersMu=None, vecConfoundersDisp=
     boolFitDrop = lsDropModel is None and strDropModel != "none"
     if strMuModel == "MM":
         raise LineagePulseError("LineagePulse ERROR: fitMMZINB() not yet supported. Contact developer.")
+    if strMuModel not in _MU:        # initialiseMuModel.R:127-130
+        raise LineagePulseError(f"ERROR fitZINB(): strMuModel={strMuModel} not recognised.")
+    if strDispModel not in _DISP:    # initialiseDispModel.R:104-107
+        raise LineagePulseError(f"ERROR fitZINB(): strDispModel={strDispModel} not recognised.")
     lsMu, lsDisp, lsDropNew = _global_models(
         counts, dfAnnotation, vecConfoundersMu, vecConfoundersDisp, vecNormConst, scaDFSplinesMu, scaDFSplinesDisp,
         strMuModel, strDispModel, strDropModel, strDropFitGroup, matPiConstPredictors,
@@ -559,6 +563,11 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
         if confs:
             if not all(c in dfAnnotation for c in confs):
                 raise LineagePulseError(f"Not all confounders given in {nm} given in dfAnnotation (columns).")
+            for c in confs:   # processSCData.R:185-190 (the reference tests vecConfoundersMu only)
+                col = dfAnnotation[c]
+                na = np.array([v is None or (isinstance(v, (float, np.floating)) and np.isnan(v)) for v in col.ravel()])
+                if na.any():
+                    raise LineagePulseError(f"Supply batch assignments for all cells and all confounders given in {nm}")
     if matPiConstPredictors is not None:
         matPiConstPredictors = np.asarray(matPiConstPredictors, dtype=np.float64)
         if matPiConstPredictors.ndim == 1:
@@ -815,10 +824,17 @@ def runLineagePulse(counts, dfAnnotation=None, vecConfoundersMu=None, vecConfoun
 # ---------------------------------------------------------------------------------------------
 # fit extraction (getFits.R): post-hoc expansions for user-selected genes
 # ---------------------------------------------------------------------------------------------
+# the reference's own messages (getFits.R:63-66, :138-141, :201-204, :267-270): three of the four name getFitsDropout()
+_ID_ERRORS = {"getNormData": "ERROR getNormData(): Not all vecGeneIDs were rownames of lsMuModel$matMuModel",
+              "getFitsMean": "ERROR getFitsDropout(): Not all vecGeneIDs were rownames of lsMuModel$matMuModel",
+              "getFitsDispersion": "ERROR getFitsDropout(): Not all vecGeneIDs were rownames of lsDispModel$matDispModel",
+              "getFitsDropout": "ERROR getFitsDropout(): Not all vecGeneIDs were rownames of lsMuModel$matMuModel"}
+
+
 def _check_ids(counts, vecGeneIDs, what):
     ids = np.asarray(vecGeneIDs)
     if not np.issubdtype(ids.dtype, np.integer) and not np.all(np.isin(ids, counts.rownames)):
-        raise LineagePulseError(f"ERROR {what}(): Not all vecGeneIDs were rownames of the model matrices")
+        raise LineagePulseError(_ID_ERRORS[what])
     return _gene_indices(counts, vecGeneIDs)
 
 

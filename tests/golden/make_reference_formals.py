@@ -1,0 +1,86 @@
+"""Generates tests/golden/reference_formals.json from the reference's R sources (run in the build container, where
+/root/reference exists; the GPU box and the tests only read the JSON):
+    python tests/golden/make_reference_formals.py [/root/reference]
+For every function of the reference's API that lineagepulse_b200.api mirrors: the formal argument names in order and,
+where the default is a single literal (number, string, TRUE / FALSE / NULL), that default.
+Also writes tests/golden/reference_messages.json: the string literals of every stop() / warning() call of the reference
+(file, line, the literals in order) -- the error behaviour the host mirror keeps."""
+import glob
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tests import r_lint  # noqa: E402
+
+FUNCTIONS = ["runLineagePulse", "processSCData", "calcNormConst", "fitLPModels", "fitModel", "fitMuDisp", "fitPi",
+             "evalLogLikMatrix", "runDEAnalysis", "testDropout", "calcPostDrop_Matrix", "getPostDrop", "getNormData",
+             "getFitsMean", "getFitsDispersion", "getFitsDropout", "simulateContinuousDataSet", "initMuModel",
+             "initDispModel", "initDropModel", "evalLogLikZINB", "evalLogLikNB", "evalImpulseModel", "evalDropoutModel"]
+
+
+def formals_with_defaults(toks, name):
+    for k in range(len(toks) - 3):
+        if toks[k][:2] == ("name", name) and toks[k + 1][:2] == ("op", "<-") and toks[k + 2][:2] == ("name", "function"):
+            depth, out, cur = 0, [], []
+            for t in toks[k + 3:]:
+                if t[0] == "open":
+                    depth += 1
+                    if depth == 1:
+                        continue
+                elif t[0] == "close":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                if depth == 1 and t[:2] == ("op", ","):
+                    out.append(cur)
+                    cur = []
+                else:
+                    cur.append(t)
+            if cur:
+                out.append(cur)
+            res = []
+            for arg in out:
+                default = None
+                if len(arg) == 3 and arg[1][:2] == ("op", "=") and arg[2][0] in ("num", "str", "name"):
+                    kind, text = arg[2][:2]
+                    if kind == "str":
+                        default = {"str": text}
+                    elif kind == "num":
+                        default = {"num": float(text.rstrip("L"))}
+                    elif text in ("TRUE", "FALSE", "NULL"):
+                        default = {"lit": text}
+                res.append([arg[0][1], default])
+            return res
+    return None
+
+
+def main():
+    root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    toks = []
+    for f in sorted(glob.glob(os.path.join(root, "R", "*.R"))):
+        toks += list(r_lint.tokens(open(f).read()))
+    out = {}
+    for fn in FUNCTIONS:
+        fm = formals_with_defaults(toks, fn)
+        assert fm is not None, fn
+        out[fn] = fm
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_formals.json")
+    json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path, {k: len(v) for k, v in out.items()})
+    msgs = []
+    for f in sorted(glob.glob(os.path.join(root, "R", "*.R"))):
+        ftoks = list(r_lint.tokens(open(f).read()))
+        for fn in ("stop", "warning"):
+            for line, args in r_lint.calls(ftoks, fn):
+                lits = [t[1] for a in args for t in a if t[0] == "str"]
+                if lits:
+                    msgs.append({"file": os.path.basename(f), "line": line, "call": fn, "literals": lits})
+    msgs.sort(key=lambda m: (m["file"], m["line"]))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_messages.json")
+    json.dump(msgs, open(path, "w"), indent=1)
+    print("wrote", path, len(msgs), "messages")
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,11 @@ def test_process_sc_data_filters_and_errors():
         lp.processSCData(X, annot, strMuModel="MM", boolVerbose=False)  # processSCData.R:231-234
     with pytest.raises(lp.LineagePulseError, match="Supply dfAnnotation"):
         lp.processSCData(X, None, strMuModel="constant", boolVerbose=False)
+    annot_b = dict(annot, batch=np.array(["b1", None, "b2", "b1"], dtype=object))
+    with pytest.raises(lp.LineagePulseError, match="Supply batch assignments for all cells"):   # processSCData.R:185-190
+        lp.processSCData(X, annot_b, vecConfoundersMu=["batch"], strMuModel="constant", boolVerbose=False)
+    with pytest.raises(lp.LineagePulseError, match="Not all confounders given in vecConfoundersMu"):
+        lp.processSCData(X, annot, vecConfoundersMu=["batch"], strMuModel="constant", boolVerbose=False)
 
 
 def test_object_accessors():
@@ -287,3 +292,89 @@ def test_r_wrappers_static_checks():
     for bad in ('f <- function(x) { g(x[[1]) }', 'x <- "abc', 'f(a, b))'):
         with pytest.raises(SyntaxError):
             r_lint.check_nesting(bad)
+
+
+def test_api_signatures_match_the_reference():
+    """tests/golden/reference_formals.json holds the formal arguments (names, order, literal defaults) of the reference's
+    R functions, extracted from /root/reference/R by tests/golden/make_reference_formals.py.  The Python mirror keeps every
+    reference argument, in the reference's order, with the reference's literal defaults (it may add arguments after them:
+    device lists, row names, a seed), and so do the R wrappers that replace reference functions."""
+    import inspect
+    import json
+    from tests import r_lint
+    from tests.helpers import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "reference_formals.json")))
+    mirrored = ["runLineagePulse", "processSCData", "calcNormConst", "fitLPModels", "fitModel", "fitMuDisp", "fitPi",
+                "evalLogLikMatrix", "runDEAnalysis", "testDropout", "calcPostDrop_Matrix", "getPostDrop", "getNormData",
+                "getFitsMean", "getFitsDispersion", "getFitsDropout", "simulateContinuousDataSet"]
+    n_defaults = 0
+    for fn in mirrored:
+        sig = inspect.signature(getattr(lp, fn)).parameters
+        names = [a for a, _ in ref[fn]]
+        assert [a for a in sig if a in names] == names, (fn, list(sig), names)      # all there, reference order
+        for a, d in ref[fn]:
+            if d is None:
+                continue
+            have = sig[a].default
+            want = d.get("str", d.get("num", {"TRUE": True, "FALSE": False, "NULL": None}.get(d.get("lit"))))
+            if fn == "fitModel" and a in ("strMuModel", "strDispModel"):
+                continue
+            assert have == want and (not isinstance(want, bool) or isinstance(have, bool)), (fn, a, have, want)
+            n_defaults += 1
+    assert n_defaults >= 50
+    # the R wrappers that replace reference functions
+    wr = open(os.path.join(ROOT, "r_shim", "R", "lpb200_wrappers.R")).read()
+    defs = r_lint.function_defs(r_lint.check_nesting(wr))
+    for fn in ("fitMuDisp", "fitPi", "evalLogLikMatrix", "fitModel", "fitLPModels"):
+        names = [a for a, _ in ref[fn]]
+        assert defs[fn][: len(names)] == names, (fn, defs[fn], names)
+    # and the reference's init functions are called by the wrappers with exactly their formals
+    toks = r_lint.check_nesting(wr)
+    for fn in ("initMuModel", "initDispModel", "initDropModel"):
+        for line, args in r_lint.calls(toks, fn):
+            given = [a[0][1] for a in args if len(a) >= 3 and a[1][:2] == ("op", "=")]
+            assert given == [a for a, _ in ref[fn]], (fn, line, given)
+
+
+def test_error_messages_are_the_reference_s():
+    """tests/golden/reference_messages.json: the string literals of every stop() / warning() of the reference (extracted by
+    tests/golden/make_reference_formals.py).  The host mirror raises the reference's own texts for the conditions it checks:
+    every literal fragment (>= 12 characters) of the messages listed here occurs verbatim in the product sources."""
+    import json
+    from tests.helpers import GOLDEN
+    msgs = json.load(open(os.path.join(GOLDEN, "reference_messages.json")))
+    src = "".join(open(os.path.join(ROOT, "lineagepulse_b200", f)).read() for f in ("api.py", "simulate.py", os.path.join("csrc", "lp_api.cu")))
+    src = re.sub(r'"\s*\n\s*f?"', "", src)     # adjacent string literals of one message
+    mirrored = {  # file -> lines of the stop() / warning() calls the mirror reproduces
+        "srcLineagePulse_calcNormConst.R": [32],
+        "srcLineagePulse_evalLogLik.R": [271, 319],
+        "srcLineagePulse_fitDropout.R": [457, 501],
+        "srcLineagePulse_fitMeanDispersion.R": [804],
+        "srcLineagePulse_getFits.R": [60, 64, 140, 202, 268, 349],
+        "srcLineagePulse_initialiseMuModel.R": [128],
+        "srcLineagePulse_initialiseDispModel.R": [105],
+        "srcLineagePulse_processSCData.R": [107, 117, 124, 134, 139, 144, 152, 167, 182, 188, 194, 202, 217, 232, 236, 240, 244],
+        "srcLineagePulse_simulateDataSet.R": [95, 101, 107, 221, 260, 281],
+    }
+    by_key = {(m["file"], m["line"]): m for m in msgs}
+    n = 0
+    for f, lines in mirrored.items():
+        for line in lines:
+            m = by_key[(f, line)]
+            for lit in m["literals"]:
+                frag = lit.strip()
+                if len(frag) >= 12:
+                    # (messages shared by several arguments are formatted with the argument's name: {nm})
+                    templ = re.sub(r"vecConfoundersMu|strDispModelFull|strDispModelRed|vecNormConstExternal|vecDispExternal|"
+                                   r"vecGeneWiseDropoutRates", "\x00", frag)
+                    pat = r"\{\w+\}".join(re.escape(part) for part in templ.split("\x00"))
+                    assert frag in src or re.search(pat, src), (f, line, frag)
+                    n += 1
+    assert n >= 45
+    # a few of them raised for real (no GPU needed)
+    X = np.ones((3, 4), dtype=np.int32)
+    for kw, text in ((dict(strMuModel="foo", strDispModel="constant"), "ERROR fitZINB(): strMuModel=foo not recognised."),
+                     (dict(strMuModel="constant", strDispModel="bar"), "ERROR fitZINB(): strDispModel=bar not recognised."),
+                     (dict(strMuModel="MM", strDispModel="constant"), "fitMMZINB() not yet supported")):
+        with pytest.raises(lp.LineagePulseError, match=re.escape(text)):
+            lp.fitModel(X, {"cell": np.arange(4)}, **kw)
