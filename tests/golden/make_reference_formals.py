@@ -84,3 +84,68 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---- names of what the boundary functions return (appended: reference_returns.json) --------------------------------
+def body_tokens(toks, name):
+    """Tokens of the body { ... } of the top-level definition `name <- function(...) { ... }`."""
+    for k in range(len(toks) - 3):
+        if toks[k][:2] == ("name", name) and toks[k + 1][:2] == ("op", "<-") and toks[k + 2][:2] == ("name", "function"):
+            depth, j = 0, k + 3
+            while True:            # skip the formals
+                if toks[j][0] == "open":
+                    depth += 1
+                elif toks[j][0] == "close":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                j += 1
+            j += 1
+            assert toks[j][:2] == ("open", "{"), name
+            start, depth = j, 0
+            while True:
+                if toks[j][0] == "open":
+                    depth += 1 if toks[j][1] != "[[" else 2
+                elif toks[j][0] == "close":
+                    depth -= 1
+                    if depth == 0:
+                        return toks[start:j + 1]
+                j += 1
+    return None
+
+
+def named_args(args):
+    return [a[0][1] for a in args if len(a) >= 3 and a[0][0] in ("name", "str") and a[1][:2] == ("op", "=")]
+
+
+def returns_main():
+    root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    toks = []
+    for f in sorted(glob.glob(os.path.join(root, "R", "*.R"))):
+        toks += list(r_lint.tokens(open(f).read()))
+    out = {}
+    for fn in ("fitMuDisp", "fitPi", "fitModel", "fitMuDispGene", "fitMuDispGeneImpulse", "fitPi_SingleCell", "fitPi_ManyCells",
+               "processSCData", "simulateContinuousDataSet"):
+        body = body_tokens(toks, fn)
+        lists = [named_args(a) for _, a in r_lint.calls(body, "list")]
+        # the returned list: the last list(...) call with named elements inside return(...)
+        rets = []
+        for line, args in r_lint.calls(body, "return"):
+            inner = [t for a in args for t in a]
+            for _, la in r_lint.calls(inner, "list"):
+                if named_args(la):
+                    rets.append(named_args(la))
+        out[fn] = rets[-1] if rets else None
+    for fn in ("runDEAnalysis", "testDropout"):
+        body = body_tokens(toks, fn)
+        frames = [named_args(a) for _, a in r_lint.calls(body, "data.frame")]
+        out[fn] = max(frames, key=len)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_returns.json")
+    json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path)
+    for k, v in out.items():
+        print(" ", k, v)
+
+
+if __name__ == "__main__":
+    returns_main()

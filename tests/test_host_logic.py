@@ -378,3 +378,40 @@ def test_error_messages_are_the_reference_s():
                      (dict(strMuModel="MM", strDispModel="constant"), "fitMMZINB() not yet supported")):
         with pytest.raises(lp.LineagePulseError, match=re.escape(text)):
             lp.fitModel(X, {"cell": np.arange(4)}, **kw)
+
+
+def test_return_names_are_the_reference_s():
+    """tests/golden/reference_returns.json: the element names of the lists the reference's boundary functions return and the
+    columns of its result tables (extracted from /root/reference/R by tests/golden/make_reference_formals.py).  The dict /
+    DataFrame literals of the Python mirror carry the same names in the same order (read off the source: the functions
+    themselves need a GPU), and the R wrappers return lists with those names."""
+    import ast
+    import json
+    from tests import r_lint
+    from tests.helpers import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "reference_returns.json")))
+    tree = ast.parse(open(os.path.join(ROOT, "lineagepulse_b200", "api.py")).read())
+    funcs = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+
+    def dict_keys(fn, pick):
+        """String keys of the dict literals inside function ``fn``; the one ``pick`` selects."""
+        ds = [[k.value for k in d.keys if isinstance(k, ast.Constant)] for d in ast.walk(funcs[fn]) if isinstance(d, ast.Dict)]
+        return pick(ds)
+
+    first_with = lambda key: (lambda ds: next(d for d in ds if key in d))   # noqa: E731
+    assert dict_keys("fitMuDisp", first_with("vecConvergence")) == ref["fitMuDisp"]
+    assert dict_keys("fitPi", first_with("vecConverged")) == ref["fitPi"]
+    assert dict_keys("_fit_result", first_with("boolConvergenceModel"))[: len(ref["fitModel"])] == ref["fitModel"]
+    assert dict_keys("processSCData", first_with("objLP")) == ref["processSCData"]
+    cols = [c for c in ref["runDEAnalysis"] if c != "stringsAsFactors"]
+    assert dict_keys("runDEAnalysis", first_with("padj_nb")) == cols
+    assert 'df["allZero"]' in ast.get_source_segment(open(os.path.join(ROOT, "lineagepulse_b200", "api.py")).read(), funcs["runDEAnalysis"])
+    sim = ast.parse(open(os.path.join(ROOT, "lineagepulse_b200", "simulate.py")).read())
+    sim_keys = [[k.value for k in d.keys if isinstance(k, ast.Constant)] for d in ast.walk(sim) if isinstance(d, ast.Dict)]
+    assert any(set(ref["simulateContinuousDataSet"]) <= set(d) for d in sim_keys)
+    # the R wrappers
+    wr = open(os.path.join(ROOT, "r_shim", "R", "lpb200_wrappers.R")).read()
+    toks = r_lint.check_nesting(wr)
+    lists = [[a[0][1] for a in args if len(a) >= 3 and a[1][:2] == ("op", "=")] for _, args in r_lint.calls(toks, "list")]
+    for fn in ("fitMuDisp", "fitPi", "fitModel"):
+        assert ref[fn] in lists, (fn, ref[fn])
