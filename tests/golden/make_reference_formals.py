@@ -3,7 +3,8 @@
     python tests/golden/make_reference_formals.py [/root/reference]
 For every function of the reference's API that lineagepulse_b200.api mirrors: the formal argument names in order and,
 where the default is a single literal (number, string, TRUE / FALSE / NULL), that default.
-Also writes tests/golden/reference_messages.json: the string literals of every stop() / warning() call of the reference
+Also writes tests/golden/reference_returns.json (element names of the lists / data frames the boundary functions return)
+and tests/golden/reference_messages.json: the string literals of every stop() / warning() call of the reference
 (file, line, the literals in order) -- the error behaviour the host mirror keeps."""
 import glob
 import json
@@ -82,9 +83,6 @@ def main():
     print("wrote", path, len(msgs), "messages")
 
 
-if __name__ == "__main__":
-    main()
-
 
 # ---- names of what the boundary functions return (appended: reference_returns.json) --------------------------------
 def body_tokens(toks, name):
@@ -148,4 +146,5 @@ def returns_main():
 
 
 if __name__ == "__main__":
+    main()
     returns_main()
