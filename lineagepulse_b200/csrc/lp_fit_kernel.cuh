@@ -52,6 +52,19 @@ __device__ __forceinline__ double lp_warp_sum(double v) {
     return v;
 }
 
+// Values the compiler must keep (in a register, or spilled) instead of re-deriving them inside the evaluation loop: at the
+// 64-register cap it otherwise rebuilds the 64-bit row pointers from (gene, pitch, base) -- nine instructions per gather -- and
+// re-reads the thread index (S2R) three times per cell (profiles/README.md R2.12).
+#ifndef LP_NO_OPAQUE
+__device__ __forceinline__ void lp_keep(int &v) { asm volatile("" : "+r"(v)); }
+template <typename T>
+__device__ __forceinline__ void lp_keep(const T *&p) { asm volatile("" : "+l"(p)); }
+#else
+__device__ __forceinline__ void lp_keep(int &) {}
+template <typename T>
+__device__ __forceinline__ void lp_keep(const T *&) {}
+#endif
+
 struct CountView {
     const void *ptr;       // gene-major, row pitch in elements
     size_t pitch;
@@ -188,7 +201,13 @@ struct FastLane {
             const bool second = own2 | (k == 1);
             const double a = (second ? F.b2 : -F.p0) * (t - (second ? F.t2 : F.t1));   // term(): -p0 (t - t1), b2 (t - t2)
             const double e = lp_exp(a);
+            // e < 1e300 (term()'s test) decided on the upper word: e >= 0 or NaN here, the bound is a little lower, and
+            // the checked reciprocal returns the same bits wherever the check-free one applies
+#ifndef LP_NO_INTCMP
+            const double s = ((unsigned)__double2hiint(e) < 0x7e37e43cu) ? lp_rcp<true>(1.0 + e) : lp_rcp<false>(1.0 + e);
+#else
             const double s = (e < 1e300) ? lp_rcp<true>(1.0 + e) : lp_rcp<false>(1.0 + e);
+#endif
             const double b1 = __shfl_sync(0xffffffffu, s, lane & 16), b2 = __shfl_sync(0xffffffffu, s, (lane & 16) | 1);
             s1 = own1 ? s : b1;
             s2 = own2 ? s : b2;
@@ -314,7 +333,11 @@ struct GenericLane {
 template <bool CL, typename LANE, typename CT, typename SH>
 __device__ void lp_eval_points(const FitArgs &A, SH &S, const CT *row, int gene, int xmax, int nk, int ntabs,
                                bool tables_allowed, double *out_vals, const double *pi_ptr, const double *l1m_ptr) {
-    const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, nwarps = blockDim.x >> 5;
+    int lane = tid & 31;
+#ifndef LP_NO_OPAQUE
+    lane = __shfl_sync(0xffffffffu, lane, lane);   // its own value: a shuffle result is not re-derived from S2R in the loop
+#endif
     const unsigned crank = CL ? lp_cluster_ctarank() : 0u, csize = CL ? lp_cluster_nctarank() : 1u;
     const int pwarp = (int)crank * nwarps + (tid >> 5), P = (int)csize * nwarps;   // physical warp of the cluster
     // (x, phi)-only part of dnbinom tabulated per distinct phi when that is cheaper than N x nk
@@ -346,22 +369,26 @@ __device__ void lp_eval_points(const FitArgs &A, SH &S, const CT *row, int gene,
     const bool active = k < nk;
     const int buf = CL ? (int)(S.epoch & 1u) : 0;
     LANE L;
+    lp_keep(row);
     L.setup(A, S, row, gene, active ? k : 0, tab_len, pi_ptr, l1m_ptr);
     const uint32_t *perm = A.C.perm + (size_t)gene * A.C.pitch;
+    lp_keep(perm);
     const int nobs = A.C.nobs[gene];
     const int stride = LP_VW * cpw;
+    // a lane without a point (k >= nk: point counts that are not powers of two) starts beyond the row and never has a term
+    const int r_lane = active ? slot : (1 << 30);
     for (int v = pwarp; v < LP_VW; v += P) {
         double acc = 0.0;
         if constexpr (LANE::kShareSigmoids) {
             // one loop for both requests, warp-uniform trip count (the shuffles of the 16-point pass need every lane)
             const bool shared_pass = (nk == 16);
-            int r = v * cpw + slot;
+            int r = v * cpw + r_lane;
             int j = (r < nobs) ? (int)perm[r] : 0;
             for (int r0 = v * cpw; r0 < nobs; r0 += stride, r += stride) {
                 const int r_next = r + stride;
                 const int j_next = (r_next < nobs) ? (int)perm[r_next] : 0;   // one iteration ahead, as below
                 const double mu = L.mean(j, lane, shared_pass);
-                if (active && r < nobs) acc += L.tail(mu, r, j);
+                if (r < nobs) acc += L.tail(mu, r, j);
                 j = j_next;
             }
         } else if (active) {
