@@ -119,7 +119,7 @@ LP_HD double lp_bd0_t(double x, double np) {
     if (fabs(x - np) < 0.1 * (x + np)) {
         double v = lp_div<FAST>(x - np, x + np);
         double s = (x - np) * v;
-#if defined(__CUDA_ARCH__) && !defined(LP_NO_INTCMP)
+#if LP_LIBM_DEVICE && !defined(LP_NO_INTCMP)   /* the device and its host mirror */
         if ((__double2hiint(s) & 0x7ff00000) == 0) return s;   // |s| < 2^-1022: the same test on the exponent field (no fp64 compare)
 #else
         if (fabs(s) < 2.2250738585072014e-308) return s;
@@ -153,7 +153,7 @@ LP_HD double lp_bd0(double x, double np) { return lp_bd0_t<false>(x, np); }
 // terms (p, q, x / np <= 2^31 / 5e-201, (phi + mu) / n >= 1e-200, (x - np) / (x + np) with 1 <= x < 2^31) lies
 // well within [1e-290, 1e290]: the check-free division and logarithm apply
 LP_HD bool lp_div_safe(double mu, double phi) {
-#if defined(__CUDA_ARCH__) && !defined(LP_NO_INTCMP)
+#if LP_LIBM_DEVICE && !defined(LP_NO_INTCMP)   /* the device and its host mirror */
     // the interval test on the upper words, [2^-332, 2^331) inside (1e-100, 1e100): one integer subtract + compare per operand
     // instead of two fp64 compares (the fp64 pipe is the binding unit); negative, NaN and infinite operands fail it as they
     // fail the comparisons, and outside the interval the checked path returns the same bits

@@ -91,3 +91,45 @@ def test_checkfree_division_is_correctly_rounded(lm):
     q, r = np.zeros(len(b)), np.zeros(len(b))
     lm.lm_div(np.ones_like(b).ctypes.data_as(dp), b.ctypes.data_as(dp), len(b), q.ctypes.data_as(dp), r.ctypes.data_as(dp))
     assert np.array_equal(r, 1.0 / b) and np.array_equal(q, 1.0 / b)
+
+
+def test_integer_range_tests_select_like_the_fp64_compares():
+    """The fit kernel decides three range tests on the upper 32-bit word instead of with fp64 compares (lp_math.cuh
+    lp_div_safe and lp_bd0_t, lp_fit_kernel.cuh FastLane::mean; profiles/README.md R2.12).  Each only selects between two
+    paths that return the same bits where both apply, so what has to hold is the implication integer test => fp64
+    condition (and equivalence for bd0's early exit).  Constants are read off the sources so the test follows them."""
+    src = {n: open(os.path.join(ROOT, "lineagepulse_b200", "csrc", n)).read() for n in ("lp_math.cuh", "lp_fit_kernel.cuh")}
+    assert "lo = 0x2b300000u, span = 0x54a00000u - 0x2b300000u" in src["lp_math.cuh"]
+    assert "(__double2hiint(s) & 0x7ff00000) == 0" in src["lp_math.cuh"]
+    assert "(unsigned)__double2hiint(e) < 0x7e37e43cu" in src["lp_fit_kernel.cuh"]
+
+    def hi(x):
+        return (np.asarray(x, dtype=np.float64).view(np.uint64) >> np.uint64(32)).astype(np.uint32)
+
+    def from_hi_lo(h, lo):
+        return ((np.asarray(h, dtype=np.uint64) << np.uint64(32)) | np.asarray(lo, dtype=np.uint64)).view(np.float64)
+
+    rng = np.random.default_rng(11)
+    # all exponents and signs, random mantissas, plus the words around every constant with extreme lower words
+    words = np.concatenate([rng.integers(0, 1 << 32, 400000, dtype=np.uint64),
+                            np.array([0x2b2fffff, 0x2b300000, 0x2b300001, 0x549fffff, 0x54a00000, 0x54a00001, 0x7e37e43b,
+                                      0x7e37e43c, 0x7e37e43d, 0x000fffff, 0x00100000, 0x800fffff, 0x80100000, 0, 0x80000000,
+                                      0x7ff00000, 0x7ff80000, 0xfff00000, 0xfff80000], dtype=np.uint64)])
+    for lo_word in (0, 0xffffffff, 1):
+        v = from_hi_lo(words, np.full(len(words), lo_word, dtype=np.uint64))
+        h = hi(v)
+        with np.errstate(invalid="ignore"):
+            # lp_div_safe: [2^-332, 2^331) lies inside (1e-100, 1e100); negative, NaN, infinite operands fail
+            int_safe = (h - np.uint32(0x2b300000)) < np.uint32(0x54a00000 - 0x2b300000)
+            fp_safe = (v > 1e-100) & (v < 1e100)
+            assert np.all(fp_safe[int_safe])
+            assert not np.any(int_safe & ~np.isfinite(v)) and not np.any(int_safe & (v <= 0))
+            # the sigmoid's reciprocal: e >= 0 or NaN arrives; the integer test must imply e < 1e300
+            int_small = h < np.uint32(0x7e37e43c)
+            assert np.all((v < 1e300)[int_small & (v >= 0)])
+            assert not np.any(int_small & np.isnan(v))
+            assert not np.any(int_small & (v < 0) & (v != 0))   # -0.0 cannot arrive from exp(); negatives never pass
+            # bd0's subnormal exit: exponent field zero <=> |s| < 2^-1022 (DBL_MIN), zero included, NaN excluded
+            int_sub = (h & np.uint32(0x7ff00000)) == 0
+            assert np.array_equal(int_sub, np.abs(v) < 2.2250738585072014e-308)
+    assert 2.0 ** -332 > 1e-100 and 2.0 ** 331 < 1e100 and hi(1e300) == 0x7e37e43c
