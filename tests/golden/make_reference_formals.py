@@ -145,6 +145,34 @@ def returns_main():
         print(" ", k, v)
 
 
+# ---- every name the R wrappers may refer to (reference_names.json) ---------------------------------------------------
+def names_main():
+    """All top-level functions of the reference with their formals [(name, has_default)], the slots of its S4 class and
+    every element name it sets (list(name = ), x$name <- ) or reads (x$name): what r_shim/R/lpb200_wrappers.R is checked
+    against by tests/test_host_logic.py::test_r_wrappers_semantic_checks (parsed with tests/r_parse.py)."""
+    from tests import r_parse
+    root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    functions, elements, slots = {}, set(), set()
+    for f in sorted(glob.glob(os.path.join(root, "R", "*.R"))):
+        prog = r_parse.parse(open(f).read())
+        for name, val in r_parse.top_level_definitions(prog).items():
+            if val.kind == "function":
+                functions[name] = [[a, d is not None] for a, d in val.a[0]]
+        elements |= r_parse.element_writes(prog)
+        elements |= {name for kind, name, _ in r_parse.element_reads(prog) if kind == "dollar"}
+        for callee, args, _ in r_parse.calls_of(prog):
+            if callee == "setClass":
+                for a, v in args:
+                    if a in ("slots", "representation") and v is not None and v.kind == "call":
+                        slots |= {n for n, _ in v.a[1] if n}
+    assert "LineagePulseObject" and "matCountsProc" in slots and "fitModel" in functions
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_names.json")
+    json.dump({"functions": functions, "slots": sorted(slots), "elements": sorted(elements)}, open(path, "w"),
+              indent=0, sort_keys=True)
+    print("wrote", path, len(functions), "functions,", len(slots), "slots,", len(elements), "element names")
+
+
 if __name__ == "__main__":
     main()
     returns_main()
+    names_main()

@@ -1,5 +1,6 @@
 """CPU-only tests of the host side: C-ABI surface, ns(), simulator, data preparation, LRT."""
 import ctypes as C
+import json
 import os
 import re
 
@@ -292,6 +293,149 @@ def test_r_wrappers_static_checks():
     for bad in ('f <- function(x) { g(x[[1]) }', 'x <- "abc', 'f(a, b))'):
         with pytest.raises(SyntaxError):
             r_lint.check_nesting(bad)
+
+
+R_BASE = {  # base / stats / methods names the wrappers may use (all exist in every R >= 3.4)
+    ".Call", "TRUE", "FALSE", "NULL", "NA", "NA_real_", "any", "as.double", "as.integer", "as.logical", "attr", "attr<-",
+    "c", "cbind", "colnames", "cumsum", "dim", "do.call", "emptyenv", "getOption", "identical", "integer", "invisible",
+    "is", "is.null", "lapply", "list", "matrix", "max", "message", "ncol", "new.env", "nrow", "numeric", "paste0",
+    "return", "rownames", "rownames<-", "seq_along", "seq_len", "stop", "sum", "unlist", "vapply", "which.max"}
+
+
+def test_r_parser_accepts_the_reference_and_rejects_broken_sources():
+    """tests/r_parse.py restates R's grammar; it is trusted only as far as it is checked: every R file of the reference
+    parses (in the build container, where /root/reference exists) and yields as many function definitions as the text
+    has `function(`; sources with the defects of a never-run file are rejected with the line."""
+    import glob
+    from tests import r_parse
+    files = sorted(glob.glob("/root/reference/R/*.R"))
+    n_fun = 0
+    for f in files:
+        src = open(f).read()
+        prog = r_parse.parse(src)
+        n_fun += sum(1 for n in r_parse.walk(prog) if n.kind == "function")
+        code = "\n".join(ln for ln in src.splitlines() if not ln.lstrip().startswith("#"))
+        assert sum(1 for n in r_parse.walk(prog) if n.kind == "function") == len(re.findall(r"\bfunction\s*\(", code)), f
+    if files:
+        assert len(files) == 23 and n_fun == 182
+    wr = open(os.path.join(ROOT, "r_shim", "R", "lpb200_wrappers.R")).read()
+    assert len(r_parse.parse(wr)) == 19          # 4 code tables + 15 functions
+    # precedence and newline rules that matter for reading the wrappers
+    e = r_parse.parse("-2^2; -1:3; !a == b; a <- b <- c; 1L * (!x) + 2L * (!y); x$y[[1]](z)@s")
+    assert e[0].kind == "unop" and e[0].a[1].a[0] == "^"
+    assert e[1].a[0] == ":" and e[1].a[1].kind == "unop"
+    assert e[2].kind == "unop" and e[2].a[1].a[0] == "=="
+    assert e[3].a[2].kind == "binop" and e[3].a[2].a[0] == "<-"
+    assert e[4].a[0] == "+" and e[5].kind == "at"
+    two = r_parse.parse("f <- function(x) {\n  y <- x\n  + 1\n}\n")   # a leading operator starts a new expression
+    assert len(two[0].a[2].a[1].a[0]) == 2
+    assert len(r_parse.parse("y <- x +\n  1\n")) == 1                   # a trailing operator continues the line
+    broken = {
+        "missing )": wr.replace("state <- new.env(parent = emptyenv())", "state <- new.env(parent = emptyenv()", 1),
+        "missing ,": wr.replace("list(n_genes = nrow(matCounts), n_cells", "list(n_genes = nrow(matCounts) n_cells", 1),
+        "dangling operator": wr.replace("ends <- cumsum(vecNBatches);", "ends <- cumsum(vecNBatches) + ;", 1),
+        "else after a closed top-level if": "f <- function(x) {\n if (x) 1\n}\nelse 2\n",
+        "chained comparison": "a < b < c\n", "unclosed {": "f <- function(x) {\n x\n", "two expressions": "a b\n",
+        "formals without ,": "f <- function(x y) x\n", "[[ closed by ]": "x[[1]\n", "open string": 'x <- "abc\n',
+        "stray )": "f(a, b))\n", "missing operand": "x <- \n", "in outside for": "a in b\n"}
+    for what, src in broken.items():
+        assert src != wr, what
+        with pytest.raises(SyntaxError):
+            r_parse.parse(src)
+
+
+def test_r_wrappers_semantic_checks():
+    """What R would only find at run time, found on the syntax tree of r_shim/R/lpb200_wrappers.R (tests/r_parse.py):
+    (1) every variable a function reads is bound -- a formal, a local, a top-level object of the file, a function of the
+    reference (tests/golden/reference_names.json, extracted from /root/reference/R) or a base-R name; (2) every call of
+    a function whose formals are known (the file's own, the reference's) matches them: no unknown or repeated argument
+    name, not too many positional ones, no formal without default left unsupplied; the do.call()s of fitLPModels
+    included; (3) every x$name / x@name that is read is a name something sets -- the reference, the wrappers, or the
+    shim's C code for the lists it returns; (4) S4 slots are slots of the reference's LineagePulseObject."""
+    from tests import r_parse
+    wr = open(os.path.join(ROOT, "r_shim", "R", "lpb200_wrappers.R")).read()
+    csrc = open(os.path.join(ROOT, "r_shim", "lp_rshim.c")).read()
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_names.json")))
+    prog = r_parse.parse(wr)
+    defs = r_parse.top_level_definitions(prog)
+    functions = {k: v for k, v in defs.items() if v.kind == "function"}
+    assert len(functions) == 15
+    # (1)
+    known = set(defs) | set(ref["functions"]) | R_BASE
+    for name, fn in functions.items():
+        unbound = {v: line for v, line in r_parse.free_variables(fn).items() if v not in known}
+        assert not unbound, f"{name}(): unbound variables {unbound}"
+    used_ref = {v for fn in functions.values() for v in r_parse.free_variables(fn) if v in ref["functions"] and v not in defs}
+    assert used_ref == {"initMuModel", "initDispModel", "initDropModel"}
+    # (2)
+    formals = {k: [(a, d) for a, d in v] for k, v in ref["functions"].items()}
+    formals.update({k: [(a, d is not None) for a, d in fn.a[0]] for k, fn in functions.items()})
+    n_checked = 0
+    for callee, args, line in r_parse.calls_of(prog):
+        if callee in formals:
+            problems = r_parse.check_call(callee, args, formals[callee])
+            assert not problems, f"line {line}: {problems}"
+            n_checked += 1
+    assert n_checked >= 40
+    fit_lp = functions["fitLPModels"]
+    lists = {}
+    for n in r_parse.walk(fit_lp):         # do.call(f, c(common, list(...))): the two lists together are the arguments
+        if n.kind == "binop" and n.a[0] == "<-" and n.a[1].kind == "name" and n.a[2].kind == "call" \
+                and n.a[2].a[0].a[0] == "list":
+            lists[n.a[1].a[0]] = n.a[2].a[1]
+    n_docall = 0
+    for callee, args, line in r_parse.calls_of(fit_lp):
+        if callee == "do.call":
+            target, packed = args[0][1].a[0], args[1][1]
+            assert packed.kind == "call" and packed.a[0].a[0] == "c" and packed.a[1][0][1].a[0] == "common"
+            merged = list(lists["common"]) + list(packed.a[1][1][1].a[1])
+            problems = r_parse.check_call(target, merged, formals[target])
+            assert not problems, f"line {line}: do.call {problems}"
+            n_docall += 1
+    assert n_docall == 2
+    # the wrappers keep every formal of the reference functions they replace, in order, with the same defaults present
+    for fn in ("fitMuDisp", "fitPi", "evalLogLikMatrix", "fitModel", "fitLPModels"):
+        want = [(a, d) for a, d in ref["functions"][fn]]
+        got = formals[fn]
+        assert got[: len(want)] == want, (fn, got, want)
+    # (3), (4)
+    set_somewhere = set(ref["elements"]) | r_parse.element_writes(prog) | set(re.findall(r'"(\w+)"', csrc))
+    for kind, name, line in r_parse.element_reads(prog):
+        if kind == "at":
+            assert name in ref["slots"] or name in ("p", "i", "x"), f"line {line}: @{name} is not a slot of LineagePulseObject / dgCMatrix"
+        else:
+            assert name in set_somewhere, f"line {line}: ${name} is read but nothing sets it"
+    for n in r_parse.walk(prog):
+        if n.kind == "binop" and n.a[0] == "<-" and n.a[1].kind == "at":
+            assert n.a[1].a[1] in ref["slots"], f"line {n.line}: slot {n.a[1].a[1]} assigned"
+    # (5) res <- .Call("routine", ...); res[[k]]: k within the list the C routine allocates
+    out_len = {}
+    for m in re.finditer(r"^SEXP\s+(lp_\w+)\s*\([^)]*\)\s*\{(.*?)^\}", csrc, re.M | re.S):
+        alloc = re.search(r"SEXP out = PROTECT\(allocVector\(VECSXP, (\d+)\)\)", m.group(2))
+        if alloc:
+            out_len[m.group(1)] = int(alloc.group(1))
+    assert out_len == {"lp_fit_mudisp": 3, "lp_fit_pi": 3, "lp_fit_model": 5, "lp_fit_models": 6, "lp_lrt": 2}
+    n_indexed = 0
+    for name, fn in functions.items():
+        results = {}
+        for n in r_parse.walk(fn):
+            if n.kind == "binop" and n.a[0] == "<-" and n.a[1].kind == "name" and n.a[2].kind == "call" \
+                    and n.a[2].a[0].kind == "name" and n.a[2].a[0].a[0] == ".Call" and n.a[2].a[1][0][1].a[0] in out_len:
+                results[n.a[1].a[0]] = n.a[2].a[1][0][1].a[0]
+        for n in r_parse.walk(fn):
+            if n.kind == "index" and n.a[0] == "[[" and n.a[1].kind == "name" and n.a[1].a[0] in results \
+                    and n.a[2][0][1].kind == "num":
+                k = int(n.a[2][0][1].a[0].rstrip("L"))
+                assert 1 <= k <= out_len[results[n.a[1].a[0]]], f"line {n.line}: {n.a[1].a[0]}[[{k}]] beyond {results[n.a[1].a[0]]}'s list"
+                n_indexed += 1
+    assert n_indexed >= 20
+    # the analyses find what they are there for
+    bad = r_parse.parse("f <- function(a) { b <- a + cc; g(b, zz = 1) }\ng <- function(x, y) x\n")
+    d = r_parse.top_level_definitions(bad)
+    assert set(r_parse.free_variables(d["f"])) == {"cc", "g"}
+    (callee, args, _), = [c for c in r_parse.calls_of(d["f"]) if c[0] == "g"]
+    assert r_parse.check_call("g", args, [("x", False), ("y", False)]) == ["g(): unknown argument 'zz'",
+                                                                          "g(): argument 'y' has no default and is not supplied"]
 
 
 def test_api_signatures_match_the_reference():
