@@ -731,6 +731,35 @@ static int fit_mudisp_gene(genefit_ctx *c, const double *theta0, const lpb200_co
     return 0;
 }
 
+/* The fit objective itself, evalLogLikMuDispGeneFit (fitMeanDispersion.R:62-222), at caller-supplied optimiser
+ * coordinates: theta is n_points x n_theta row-major.  For the tests that compare it with the reference's own R text
+ * (tests/golden/reference_exec.json); the drop-out handling is fitMuDispGene's (:887-892 fixed pi for "logistic"). */
+int lporacle_objective_mudisp(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
+                              const lpb200_params *p, int gene, const double *theta, int n_points, double *out) {
+    if (!counts || !d || !m || !theta || !out || gene < 0 || gene >= d->n_genes) return LPB200_E_ARG;
+    int N = d->n_cells, n = n_theta(d, m);
+    double *buf = (double *)malloc(sizeof(double) * 4 * (size_t)N);
+    if (!buf) return LPB200_E_ARG;
+    genefit_ctx gc;
+    gc.x = counts + (size_t)gene * N;
+    gc.d = d;
+    gc.m = m;
+    gc.mat_drop = p ? p->mat_drop : NULL;
+    gc.gene = gene;
+    gc.mu = buf;
+    gc.disp = buf + N;
+    gc.pi = buf + 2 * (size_t)N;
+    gc.pi_fixed = NULL;
+    if (m->drop_model == LPB200_DROP_LOGISTIC) {
+        double *pf = buf + 3 * (size_t)N;
+        for (int j = 0; j < N; j++) pf[j] = pi_at(d, m, p->mat_drop, gene, j, NAN);
+        gc.pi_fixed = pf;
+    }
+    for (int k = 0; k < n_points; k++) out[k] = genefit_cost(n, theta + (size_t)k * n, &gc);
+    free(buf);
+    return 0;
+}
+
 /* pack natural-scale guesses into theta (fitMeanDispersion.R:349-364); for impulse the caller
  * supplies the 7 mu coordinates already in optimiser space (:621-622) */
 static void pack_theta(const lpb200_design *d, const lpb200_model *m, const gene_nat *g,

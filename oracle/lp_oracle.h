@@ -31,6 +31,9 @@ int lporacle_impulse_starts(const int32_t *counts, const lpb200_design *d, doubl
 int lporacle_fit_mudisp(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
                         lpb200_params *p, const lpb200_control *c, double *ll, int32_t *conv,
                         uint64_t *fn_evals, int nthreads);
+/* evalLogLikMuDispGeneFit (fitMeanDispersion.R:62-222) of one gene at n_points parameter vectors (row-major) */
+int lporacle_objective_mudisp(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
+                              const lpb200_params *p, int gene, const double *theta, int n_points, double *out);
 int lporacle_fit_pi(const int32_t *counts, const lpb200_design *d, const lpb200_model *m,
                     lpb200_params *p, const lpb200_control *c, double *ll, int32_t *conv,
                     uint64_t *fn_evals, int nthreads);

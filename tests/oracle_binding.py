@@ -139,6 +139,17 @@ class Oracle:
         params.sync_back()
         return dict(ll=ll, conv=conv, fn_evals=ev.value, rc=rc)
 
+    def objective_mudisp(self, counts, design, model, params, gene, thetas):
+        """evalLogLikMuDispGeneFit of one gene at the rows of thetas (optimiser coordinates)."""
+        c, cp = self._counts(counts)
+        th = np.ascontiguousarray(thetas, dtype=np.float64)
+        out = np.zeros(th.shape[0])
+        ps = params.as_struct()
+        self._check(self.lib.lporacle_objective_mudisp(cp, C.byref(design.struct), C.byref(model), C.byref(ps), int(gene),
+                                                       th.ctypes.data_as(A.c_double_p), th.shape[0],
+                                                       out.ctypes.data_as(A.c_double_p)))
+        return out
+
     def fit_pi(self, counts, design, model, params, control=None):
         c, cp = self._counts(counts)
         control = control or A.default_control()

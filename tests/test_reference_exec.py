@@ -1,0 +1,159 @@
+"""The CPU oracle against outputs of the reference's OWN R source (CPU-only).
+
+tests/golden/reference_exec.json was made by tests/golden/make_reference_exec_golden.py: the reference's R files, parsed by
+tests/r_parse.py and executed by tests/r_eval.py -- fitModel's EM loop, the init*Model functions, fitMuDisp /
+fitMuDispGene / fitMuDispGeneImpulse, fitPi, evalLogLikMatrix, the decompress* functions and evalLogLikMuDispGeneFit run
+as written; only R's compiled builtins (arithmetic, sum, optim's vmmin, dnbinom, ns, lm) are restated.  This pins what a
+restatement gets wrong: parameter unpacking order, clamps, start values, the three-start selection, the EM stopping rule,
+which drop-out rates are held fixed during a gene's fit."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from lineagepulse_b200 import _cabi as A
+from lineagepulse_b200.splines import ns
+from tests.helpers import golden, model, rel
+
+CASES = golden("reference_exec.json")["cases"]
+
+
+def _design(case):
+    d, how = case["data"], case["how"]
+    X = np.ascontiguousarray(d["counts"], dtype=np.int32)
+    G, N = X.shape
+    t = np.asarray(d["t"], dtype=np.float64)
+    sf = np.asarray(d["sf"], dtype=np.float64)
+    groups = d["groups"] if "groups" in (how["strMuModel"], how["strDispModel"]) else None
+    design = A.DesignData(
+        G, N, size_factors=None if np.all(sf == 1.0) else sf, pseudotime=t, groups=groups,
+        spline_basis_mu=ns(t, int(how["scaDFSplinesMu"])) if how["strMuModel"] == "splines" else None,
+        spline_basis_disp=ns(t, int(how["scaDFSplinesDisp"])) if how["strDispModel"] == "splines" else None,
+        impulse_basis=ns(t, 4), confounders_mu=[d["batch"]] if how.get("vecConfoundersMu") else None,
+        confounders_disp=[d["batch"]] if how.get("vecConfoundersDisp") else None)
+    m = model(how["strMuModel"], how["strDispModel"], how["strDropModel"], how.get("strDropFitGroup", "PerCell"))
+    return X, design, m
+
+
+def _fit(oracle, case):
+    X, design, m = _design(case)
+    how = case["how"]
+    fit_drop = how["strDropModel"] != "none" and "matDropoutLinModel" not in how
+    p = A.ParamsData(design, m)
+    if "matDropoutLinModel" in how:
+        p.mat_drop = np.asfortranarray(np.asarray(how["matDropoutLinModel"], dtype=np.float64))
+    r = oracle.fit_model(X, design, m, p, fit_drop)
+    return X, design, m, p, r
+
+
+FITS = [c for c in CASES if "reference" in c]
+
+
+@pytest.mark.parametrize("case", FITS, ids=[c["name"] for c in FITS])
+def test_oracle_reproduces_the_executed_reference(oracle, case):
+    X, design, m, p, r = _fit(oracle, case)
+    ref = case["reference"]
+    impulse = case["how"]["strMuModel"] == "impulse"
+    mpmath_run = "mpmath" in case["name"]
+    em = np.asarray(ref["vecEMLogLikModel"])
+    assert r["n_iter"] == len(em) and bool(r["converged"]) == ref["boolConvergenceModel"]
+    ll = oracle.eval_loglik(X, design, m, p)
+    ll_ref = np.asarray(ref["vecLL"])
+    if impulse and "numpy QR" in case["name"]:
+        # The start values come from an lm() fit; two correct least-squares solvers differ in its last bit (4e-16 here,
+        # test_impulse_start_values_of_the_executed_reference) and BFGS from three starts over a 9-parameter surface on
+        # 26 cells amplifies that bit (tests/test_oracle_sensitivity.py).  With the solver's operation order made equal
+        # (the other impulse cases) every gene agrees to the last bit, so this spread is conditioning, not a difference
+        # of algorithm: about half the genes land on the same optimum, the rest on neighbouring ones.
+        assert np.mean(rel(ll, ll_ref) < 1e-6) >= 0.3 and np.max(rel(ll, ll_ref)) < 5e-3
+        assert rel(r["em_ll"][0], em[0]) < 1e-3
+        return
+    if not mpmath_run:
+        # same libm, same dnbinom, same long-double sums, same vmmin: the reference's R text and the oracle take every
+        # optimiser decision alike -- log-likelihoods, parameters and the EM trajectory are equal to the last bit
+        assert np.array_equal(ll, ll_ref), np.max(rel(ll, ll_ref))
+        assert np.array_equal(r["em_ll"][: len(em)], em)
+        assert np.array_equal(p.mat_mu, np.asarray(ref["matMuModel"], dtype=np.float64).reshape(p.mat_mu.shape))
+        assert np.array_equal(p.mat_disp, np.asarray(ref["matDispModel"], dtype=np.float64).reshape(p.mat_disp.shape))
+        if ref["lsmatBatchModelMu"]:
+            assert np.array_equal(p.batch_mu[0], np.asarray(ref["lsmatBatchModelMu"][0]))
+        if ref["lsmatBatchModelDisp"]:
+            assert np.array_equal(p.batch_disp[0], np.asarray(ref["lsmatBatchModelDisp"][0]))
+        if ref["matDropoutLinModel"] is not None and "matDropoutLinModel" not in case["how"]:
+            assert np.array_equal(p.mat_drop, np.asarray(ref["matDropoutLinModel"], dtype=np.float64).reshape(p.mat_drop.shape))
+        return
+    tol_ll, tol_par = 1e-8, 1e-5        # dnbinom by mpmath instead of the restated nmath routine: ~1e-16 per term
+    assert np.max(rel(r["em_ll"][: len(em)], em)) < tol_ll
+    assert np.max(rel(ll, ll_ref)) < tol_ll
+    mu_ref = np.asarray(ref["matMuModel"], dtype=np.float64).reshape(p.mat_mu.shape)
+    disp_ref = np.asarray(ref["matDispModel"], dtype=np.float64).reshape(p.mat_disp.shape)
+    ok = disp_ref.max(axis=1) < 100          # a dispersion that ran off to the Poisson limit is flat, not determined
+    if case["how"]["strMuModel"] == "splines":
+        assert np.max(np.abs(p.mat_mu - mu_ref)) < 1e-4
+    else:
+        assert np.max(rel(p.mat_mu, mu_ref)) < tol_par * 10
+    if case["how"]["strDispModel"] != "splines":
+        assert np.max(rel(p.mat_disp[ok], disp_ref[ok])) < tol_par * 100
+    if ref["lsmatBatchModelMu"]:
+        assert np.max(rel(p.batch_mu[0], np.asarray(ref["lsmatBatchModelMu"][0]))) < 1e-4
+    if ref["lsmatBatchModelDisp"]:
+        assert np.max(rel(p.batch_disp[0][ok], np.asarray(ref["lsmatBatchModelDisp"][0])[ok])) < 1e-3
+    if ref["matDropoutLinModel"] is not None and "matDropoutLinModel" not in case["how"]:
+        drop_ref = np.asarray(ref["matDropoutLinModel"], dtype=np.float64).reshape(p.mat_drop.shape)
+        assert np.max(np.abs(p.mat_drop - drop_ref) / np.maximum(1.0, np.abs(drop_ref))) < 1e-4
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if "objective" in c], ids=[c["name"] for c in CASES if "objective" in c])
+def test_objective_equals_the_executed_reference(oracle, case):
+    """evalLogLikMuDispGeneFit of the reference (executed, dnbinom by 50-digit mpmath) at random, clamped and extreme
+    parameter vectors against the oracle's objective: unpacking order, every clamp, the -700 floor, which drop-out rates
+    enter."""
+    X, design, m = _design(case)
+    how, ref = case["how"], case["reference"]
+    p = A.ParamsData(design, m)
+    if m.drop_model != A.DROP_NONE:
+        src = how.get("matDropoutLinModel", ref["matDropoutLinModel"])
+        p.mat_drop = np.asfortranarray(np.asarray(src, dtype=np.float64).reshape(design.n_cells, -1))
+    worst = 0.0
+    for item in case["objective"]:
+        got = oracle.objective_mudisp(X, design, m, p, item["gene"], np.asarray(item["thetas"]))
+        want = np.asarray(item["values"])
+        worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))))
+    # R's dnbinom loses digits at the 1e10 dispersion clamp (n - x cancellation, ~1e-7 relative);
+    # the extreme vectors sit exactly there, the random ones do not
+    assert worst < 1e-6, worst
+    typical = 0.0
+    for item in case["objective"]:
+        th = np.asarray(item["thetas"])
+        keep = np.max(np.abs(th), axis=1) < 20
+        if keep.any():
+            got = oracle.objective_mudisp(X, design, m, p, item["gene"], th[keep])
+            want = np.asarray(item["values"])[keep]
+            typical = max(typical, float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))))
+    assert typical < 1e-12, typical
+
+
+def test_impulse_start_values_of_the_executed_reference(oracle):
+    """initialiseImpulseParameters (initialiseImpulseParameters.R:29-111) executed from the reference's text, lm() by an
+    independent least-squares solver, against the oracle's start values."""
+    case = next(c for c in CASES if "starts" in c)
+    X, design, m = _design(case)
+    peak, valley = oracle.impulse_starts(X, design)
+    for i, st in enumerate(case["starts"]):
+        assert np.max(rel(peak[i], st["peak"])) < 1e-13 and np.max(rel(valley[i], st["valley"])) < 1e-13
+
+
+@pytest.mark.skipif(not glob.glob("/root/reference/R/*.R"), reason="the reference's sources exist in the build container only")
+def test_committed_golden_is_what_the_reference_text_produces(oracle):
+    """Re-executes two cheap cases from /root/reference and compares with the committed JSON (bit for bit)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_exec_golden as gen
+    ref = gen.Reference("/root/reference", dnbinom=lambda x, s, mu: oracle.dnbinom_mu_log(x, s, mu))
+    for name in ("H0 constant ZINB, drop-out EM (fit A)", "dispersion groups + dispersion batch confounder, NB"):
+        case = next(c for c in CASES if c["name"] == name)
+        data = {k: np.asarray(v) for k, v in case["data"].items()}
+        _, out = gen.fit_model(ref, data, **case["how"])
+        for key in ("matMuModel", "matDispModel", "vecLL", "vecEMLogLikModel", "matDropoutLinModel", "lsmatBatchModelDisp"):
+            assert out[key] == case["reference"][key], (name, key)
