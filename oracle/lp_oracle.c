@@ -15,9 +15,12 @@
  *   - stats::lm(y ~ 0 + B) = least squares by QR;
  *   - stats::pchisq(lower.tail=FALSE), stats::p.adjust(method="BH");
  *   - base::sum accumulates in long double.
- * PARITY STATUS: parity unpinned by the reference (no goldens, R not runnable);
- * pinned against mpmath golden values, the ?optim Rosenbrock known answers and
- * analytic identities in tests/.
+ * PARITY STATUS: the reference ships no golden vectors and R is not installed, so
+ * parity is unpinned by an R session.  Pinned instead against (1) the reference's own
+ * R source executed by tests/r_eval.py (fitModel and everything under it, unmodified;
+ * tests/golden/reference_exec.json: reproduced to the last bit, tests/test_reference_exec.py)
+ * with only R's compiled builtins restated, and (2) for those builtins: mpmath and scipy
+ * golden values, the ?optim Rosenbrock known answers and analytic identities in tests/.
  */
 #define _GNU_SOURCE
 #include <float.h>

@@ -5,11 +5,13 @@
  * call this; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs use it, as the checker / reported CPU baseline.
  *
- * PARITY STATUS: "parity unpinned by the reference" -- the reference ships no
- * tests, fixtures or golden vectors and R cannot be run here
- * (F3).  The pins this oracle is checked against are ours: 50-digit mpmath
- * values (tests/golden/), the ?optim Rosenbrock known answers, and analytic
- * identities.
+ * PARITY STATUS: the reference ships no tests, fixtures or golden vectors
+ *  and R cannot be run here (F3): "parity unpinned" by an R session.
+ * The pins this oracle is checked against: the reference's own R source text
+ * executed by tests/r_eval.py (outputs committed as tests/golden/reference_exec.json
+ * and reproduced to the last bit), and for the R-base builtins that evaluator
+ * restates: 50-digit mpmath and scipy values (tests/golden/), the ?optim Rosenbrock
+ * known answers, and analytic identities.
  */
 #ifndef LP_ORACLE_H
 #define LP_ORACLE_H

@@ -157,3 +157,37 @@ def test_committed_golden_is_what_the_reference_text_produces(oracle):
         _, out = gen.fit_model(ref, data, **case["how"])
         for key in ("matMuModel", "matDispModel", "vecLL", "vecEMLogLikModel", "matDropoutLinModel", "lsmatBatchModelDisp"):
             assert out[key] == case["reference"][key], (name, key)
+
+
+def test_kernel_mirror_against_the_executed_reference(oracle):
+    """The GPU fit kernel's host mirror (tests/csrc/mirror_harness.cpp: bit for bit the kernel, asserted on the GPU) on
+    the inputs of the executed reference.  What separates the two is arithmetic mode only -- device exp / log and 32
+    partial sums against libm and a long-double running sum -- so the well-conditioned fits land on the reference's
+    optimum (north_star: log-likelihood 1e-6, parameters 1e-4) and the impulse fits on it or a neighbouring one."""
+    from tests.helpers import best_start, theta0_items
+    from tests.mirror_harness import Mirror
+    mir = Mirror()
+    n = 0
+    for case in FITS:
+        how = case["how"]
+        if how["strDropModel"] != "none" and "matDropoutLinModel" not in how:
+            continue                       # the drop-out EM is not a fit-kernel item
+        if "mpmath" in case["name"] or "oracle's operation order" in case["name"]:
+            continue
+        X, design, m = _design(case)
+        p0 = oracle.init_params(X, design, m)
+        drop = None
+        if "matDropoutLinModel" in how:
+            drop = np.asfortranarray(np.asarray(how["matDropoutLinModel"], dtype=np.float64))
+            p0.mat_drop = drop
+        th0, n_starts = theta0_items(oracle, X, design, m, p0)
+        mr = mir.fit_items(design, m, X, th0, n_starts, drop=drop)
+        _, ll = best_start(mr["ll_items"], n_starts)
+        ll_ref = np.asarray(case["reference"]["vecLL"])
+        r = rel(ll, ll_ref)
+        if how["strMuModel"] == "impulse":
+            assert np.mean(r < 1e-6) >= 0.3 and r.max() < 5e-3, (case["name"], r)
+        else:
+            assert r.max() < 1e-8, (case["name"], r)
+        n += 1
+    assert n == 7
