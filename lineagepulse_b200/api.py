@@ -574,6 +574,11 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
             matPiConstPredictors = matPiConstPredictors.reshape(-1, 1)
         if matPiConstPredictors.shape[0] != G:
             raise LineagePulseError("ERROR: Some genes named in rows of counts do not occur in rows of matPiConstPredictors.")
+    if isinstance(vecNormConstExternal, dict):
+        # R's named vector (processSCData.R:215-221, :292): looked up by the cell names of the count matrix
+        if not all(c in vecNormConstExternal for c in colnames):
+            raise LineagePulseError("ERROR IN INPUT DATA CHECK: Not all cells in counts are given in vecNormConstExternal")
+        vecNormConstExternal = np.array([vecNormConstExternal[c] for c in colnames], dtype=np.float64)
     if vecNormConstExternal is not None and len(vecNormConstExternal) != N:
         raise LineagePulseError("ERROR IN INPUT DATA CHECK: Not all cells in counts are given in vecNormConstExternal")
     if rownames is None:

@@ -160,6 +160,31 @@ def fit_model(ref, data, strMuModel, strDispModel, strDropModel, strDropFitGroup
     return res, out
 
 
+def run_lineagepulse(ref, data, **kw):
+    """The public call, main_LineagePulse.R:219-328: processSCData (checks, sparse conversion, all-zero filters),
+    calcNormConst, fitLPModels (fits A-D), runDEAnalysis (LRT, BH, results table with its NA rows)."""
+    mat, df, sf = r_inputs(data)
+    df.attrs = {"class": "data.frame", "row.names": list(df.v[0].v)}
+    args = dict(counts=mat, dfAnnotation=df, boolVerbose=B(False))
+    for k, v in kw.items():
+        args[k] = S(v) if isinstance(v, (str, list)) else (B(v) if isinstance(v, bool) else D(v))
+    if not np.all(np.asarray(data["sf"]) == 1.0):
+        args["vecNormConstExternal"] = sf
+    t0 = time.time()
+    obj = ref.call("runLineagePulse", **args)
+    slot = lambda name: obj.v[obj.names.index(name)]     # noqa: E731
+    res = slot("dfResults")
+    conv = slot("lsFitConvergence")
+    table = {}
+    for name, col in zip(res.names, res.v):
+        table[name] = [None if (isinstance(x, float) and x != x) else (x.item() if hasattr(x, "item") else x) for x in col.v]
+    return dict(dfResults=table, row_names=res.attrs["row.names"],
+                vecEMLogLikH0=[v for v in as_py(conv.get("vecEMLogLikH0")) if v == v],
+                vecEMLogLikH1=[v for v in as_py(conv.get("vecEMLogLikH1")) if v == v],
+                genes_kept=list(slot("matCountsProc").dimnames[0]), cells_kept=list(slot("matCountsProc").dimnames[1]),
+                strReport=slot("strReport").v[0], seconds=round(time.time() - t0, 1))
+
+
 def objective_vectors(ref, data, res, rng, n_random=6):
     """evalLogLikMuDispGeneFit (fitMeanDispersion.R:62-222) of every gene at random and at extreme parameter vectors,
     called exactly as fitMuDispGene calls it (:367-383), dnbinom by mpmath."""
@@ -274,6 +299,22 @@ def main():
     how = dict(strMuModel="constant", strDispModel="constant", strDropModel="logistic", strDropFitGroup="ForAllCells")
     r = fit_model(fast, d3, **how)
     add("H0 constant ZINB, ForAllCells drop-out EM", d3, how, r)
+
+    # the public API end to end
+    d4 = make_data(21, G=8, N=24, size_factors=True)
+    d4["counts"][3, :] = 0          # an all-zero gene and an all-zero cell: filtered, NA row in dfResults
+    d4["counts"][:, 5] = 0
+    for name, kw in (("splines (df 4) vs constant", dict(strMuModel="splines", scaDFSplinesMu=4, strDropModel="logistic")),
+                     ("impulse vs constant", dict(strMuModel="impulse", strDropModel="logistic")),
+                     ("groups + batch confounder vs constant + batch", dict(strMuModel="groups", vecConfoundersMu=["batch"],
+                                                                            strDropModel="logistic")),
+                     ("groups vs constant, noise model on H1", dict(strMuModel="groups", strDropModel="logistic",
+                                                                   boolEstimateNoiseBasedOnH0=False)),
+                     ("splines with dispersion splines under H1", dict(strMuModel="splines", scaDFSplinesMu=4, strDispModelFull="splines",
+                                                                       scaDFSplinesDisp=3, strDropModel="logistic"))):
+        out = run_lineagepulse(fast, d4, **kw)
+        cases.append(dict(name="runLineagePulse: " + name, how=kw, data={k: np.asarray(v).tolist() for k, v in d4.items()}, api=out))
+        print("runLineagePulse:", name, out["seconds"], "s; p =", out["dfResults"]["p"][:3], flush=True)
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_exec.json")
     json.dump(dict(note="outputs of the reference's own R source executed by tests/r_eval.py; see make_reference_exec_golden.py",

@@ -479,13 +479,26 @@ def install(I):
         return RVec(data, dim=(nr, nc))
 
     B["dim"] = lambda I, a, e: None if a[0][1] is None or not isinstance(a[0][1], RVec) or a[0][1].dim is None else RVec(np.array(a[0][1].dim, dtype=np.int64))
-    B["nrow"] = lambda I, a, e: None if a[0][1].dim is None else RVec(np.array([a[0][1].dim[0]], dtype=np.int64))
-    B["ncol"] = lambda I, a, e: None if a[0][1].dim is None else RVec(np.array([a[0][1].dim[1]], dtype=np.int64))
+    def _extent(axis):
+        def go(I, args, env):
+            x = args[0][1]
+            if isinstance(x, RList):
+                if x.attrs.get("class") != "data.frame":
+                    return None
+                return RVec(np.array([len(x.v[0]) if axis == 0 and x.v else (0 if axis == 0 else len(x))], dtype=np.int64))
+            return None if x.dim is None else RVec(np.array([x.dim[axis]], dtype=np.int64))
+        return go
+    B["nrow"], B["ncol"] = _extent(0), _extent(1)
     B["t"] = lambda I, a, e: RVec(a[0][1].mat().T.reshape(-1, order="F"), dim=a[0][1].dim[::-1]) if a[0][1].dim else RVec(a[0][1].v, dim=(1, len(a[0][1])))
 
     def dimnames_get(axis):
         def go(I, args, env):
             x = args[0][1]
+            if isinstance(x, RList):
+                if x.attrs.get("class") != "data.frame":
+                    return None
+                nm = x.attrs.get("row.names") if axis == 0 else x.names
+                return None if nm is None else RVec(np.array(list(nm), dtype=object))
             if x is None or x.dimnames is None or x.dimnames[axis] is None:
                 return None
             return RVec(np.array(x.dimnames[axis], dtype=object))
@@ -494,6 +507,12 @@ def install(I):
     def dimnames_set(axis):
         def go(I, args, env):
             x, value = args[0][1], args[-1][1]
+            if isinstance(x, RList) and x.attrs.get("class") == "data.frame" and value is not None:
+                out = RList(x.v, x.names if axis == 0 else [str(s_) for s_ in value.v])
+                out.attrs = dict(x.attrs)
+                if axis == 0:
+                    out.attrs["row.names"] = [str(s_) for s_ in value.v]
+                return out
             if value is None and (isinstance(x, RList) or x.dim is None):      # `dimnames<-`: nothing to remove
                 return x
             dn = list(x.dimnames or (None, None))
@@ -583,7 +602,10 @@ def install(I):
     def _(I, args, env):
         x, table = args[0][1], args[1][1]
         tl = table.v.tolist()
-        return RVec(np.array([tl.index(v) + 1 if v in tl else -1 for v in x.v.tolist()], dtype=np.int64))
+        pos = [tl.index(v) + 1 if v in tl else None for v in x.v.tolist()]
+        if any(q is None for q in pos):           # NA_integer_ is modelled as a double NaN
+            return RVec(np.array([np.nan if q is None else float(q) for q in pos]))
+        return RVec(np.array(pos, dtype=np.int64))
 
     B["unique"] = lambda I, a, e: RVec(np.array(list(dict.fromkeys(a[0][1].v.tolist())), dtype=a[0][1].v.dtype))
     B["rev"] = lambda I, a, e: RVec(a[0][1].v[::-1].copy())
@@ -797,6 +819,72 @@ def install(I):
             raise RError("array: more than two dimensions are not modelled")
         n = int(np.prod(d))
         return RVec(np.resize(a["data"].v, n), dim=tuple(d) if len(d) == 2 else None)
+
+    I.classes = {}
+
+    @reg("setClass")
+    def _(I, args, env):
+        a = _args(args, ["Class", "representation", "slots", "contains"])
+        slots = a.get("slots", a.get("representation"))
+        I.classes[a["Class"].v[0]] = list(slots.names)
+        return None
+
+    @reg("new")
+    def _(I, args, env):
+        cls = args[0][1].v[0]
+        given = {a: v for a, v in args[1:]}
+        slots = I.classes.get(cls, list(given))
+        for a in given:
+            if a not in slots:
+                raise RError(f"invalid name for slot of class \u201c{cls}\u201d: {a}")
+        out = RList([given.get(sl) for sl in slots], slots)       # unspecified slots: the (NULL) prototype
+        out.attrs["class"] = cls
+        return out
+
+    @reg("is")
+    def _(I, args, env):
+        a = _args(args, ["object", "class2"])
+        x, cls = a["object"], a["class2"].v[0]
+        if isinstance(x, RList):
+            return RVec(np.array([x.attrs.get("class") == cls or (cls == "list" and "class" not in x.attrs)]))
+        if isinstance(x, RVec):
+            kinds = {"character": x.v.dtype == object, "numeric": x.v.dtype.kind in "if", "logical": x.v.dtype == bool,
+                     "matrix": x.dim is not None}
+            return RVec(np.array([bool(kinds.get(cls, False))]))
+        return RVec(np.array([False]))
+
+    B["is.logical"] = lambda I, a, e: RVec(np.array([isinstance(a[0][1], RVec) and a[0][1].v.dtype == bool]))
+    B["data.matrix"] = lambda I, a, e: a[0][1]
+    B["register"] = B["SerialParam"] = B["MulticoreParam"] = lambda I, a, e: None
+    B["packageDescription"] = lambda I, a, e: RVec(np.array(["(executed from source)"], dtype=object))
+    B["%%"] = lambda I, a, e: I._like(a[0][1], np.mod(*I._recycle(a[0][1].v, a[1][1].v)))
+    B["%/%"] = lambda I, a, e: I._like(a[0][1], np.floor_divide(*I._recycle(a[0][1].v, a[1][1].v)))
+
+    @reg("dimnames")
+    def _(I, args, env):
+        x = args[0][1]
+        if x.dimnames is None:
+            return None
+        return RList([None if d is None else RVec(np.array(d, dtype=object)) for d in x.dimnames])
+
+    @reg("sparseMatrix")
+    def _(I, args, env):
+        a = _args(args, ["i", "j", "p", "x", "dims", "dimnames", "symmetric", "index1"])
+        one = 1 if ("index1" not in a or truth(a["index1"])) else 0
+        nr, nc = (int(v) for v in a["dims"].v)
+        m = np.zeros((nr, nc))
+        m[a["i"].v.astype(np.int64) - one, a["j"].v.astype(np.int64) - one] = a["x"].v
+        dn = a.get("dimnames")
+        return RVec(m.reshape(-1, order="F"), dim=(nr, nc),
+                    dimnames=None if dn is None else tuple(None if d is None else list(d.v) for d in dn.v))
+
+    @reg("data.frame")
+    def _(I, args, env):
+        cols = [(a, v) for a, v in args if a not in ("stringsAsFactors", "row.names", "check.names")]
+        n = max(len(v) for _, v in cols)
+        out = RList([RVec(np.resize(v.v, n)) for _, v in cols], [a for a, _ in cols])
+        out.attrs = {"class": "data.frame", "row.names": [str(k + 1) for k in range(n)]}
+        return out
 
     B["attr<-"] = lambda I, a, e: a[0][1]
     B["invisible"] = lambda I, a, e: a[0][1] if a else None

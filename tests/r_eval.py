@@ -199,6 +199,8 @@ class Interp:
                     if isinstance(val, Closure):
                         val.name = e.a[1].a[0]
                     self.globals.set(e.a[1].a[0], val)
+            elif e.kind == "call" and e.a[0].kind == "name" and e.a[0].a[0] == "setClass":
+                self.eval(e, self.globals)            # records the slots new() fills
             elif not only_definitions:
                 self.eval(e, self.globals)
 
@@ -308,6 +310,13 @@ class Interp:
             if isinstance(obj, RList):
                 return obj.get(n.a[1], exact=False)
             raise RError("$ operator is invalid for atomic vectors")
+        if k == "at":
+            obj = self.eval(n.a[0], env)
+            if not isinstance(obj, RList) or "class" not in obj.attrs:
+                raise RError("trying to get slot \"%s\" of an object that is not an S4 object" % n.a[1])
+            if obj.names is None or n.a[1] not in obj.names:
+                raise RError("no slot of name \"%s\" for this object" % n.a[1])
+            return obj.v[obj.names.index(n.a[1])]
         if k == "ns":
             if n.a[1] in self.builtins:
                 return self.builtins[n.a[1]]
@@ -597,6 +606,8 @@ class Interp:
             if len(p) != 1 or p[0] >= len(obj):
                 raise RError("subscript out of bounds")
             return RVec(obj.v[p])
+        if isinstance(obj, RList) and obj.attrs.get("class") == "data.frame" and len(pos_args) == 2:
+            return self._index_data_frame(obj, pos_args[0], pos_args[1])
         if isinstance(obj, RList):
             p = self._positions(pos_args[0], len(obj), obj.names)
             return RList([obj.v[k] if k < len(obj) else None for k in p],
@@ -631,6 +642,32 @@ class Interp:
             out = obj.v[p]
         return RVec(out, names=[obj.names[k] for k in p] if obj.names is not None and np.all(inside) else None)
 
+    def _index_data_frame(self, df, rows, cols):
+        """df[rows, cols]: rows may hold NA (a row of NA, as match() produces for absent keys)."""
+        rn = df.attrs.get("row.names")
+        n = len(df.v[0]) if df.v else 0
+        if rows is MISSING:
+            pr = np.arange(n, dtype=np.float64)
+        elif rows.v.dtype.kind == "f" and np.any(np.isnan(rows.v)):
+            pr = rows.v - 1
+        else:
+            pr = self._positions(rows, n, rn).astype(np.float64)
+        pc = self._positions(cols, len(df), df.names)
+        out_cols = []
+        for k in pc:
+            col = df.v[k]
+            if col.v.dtype == object:
+                vals = np.array([col.v[int(r)] if r == r else None for r in pr], dtype=object)
+            else:
+                vals = np.array([col.v[int(r)] if r == r else np.nan for r in pr], dtype=np.float64 if np.any(pr != pr) else col.v.dtype)
+            out_cols.append(RVec(vals))
+        if cols is not MISSING and len(pc) == 1:
+            return out_cols[0]
+        out = RList(out_cols, [df.names[k] for k in pc])
+        out.attrs = {"class": "data.frame",
+                     "row.names": [rn[int(r)] if (rn is not None and r == r) else "NA" for r in pr] if rn is not None else None}
+        return out
+
     def assign(self, target, value, target_env, env):
         k = target.kind
         if k in ("name", "str"):
@@ -646,6 +683,15 @@ class Interp:
             if not isinstance(cur, RList):
                 raise RError("$<- on an atomic vector")
             return self.assign(obj_node, cur.set(target.a[1], value), target_env, env)
+        if k == "at":
+            obj_node = target.a[0]
+            cur = self.eval(obj_node, env)
+            if not isinstance(cur, RList) or cur.names is None or target.a[1] not in cur.names:
+                raise RError("no slot of name \"%s\" for this object" % target.a[1])
+            out = RList(cur.v, cur.names)
+            out.attrs = dict(cur.attrs)
+            out.v[out.names.index(target.a[1])] = value
+            return self.assign(obj_node, out, target_env, env)
         if k == "index":
             obj_node = target.a[1]
             cur = self._current(obj_node, target_env, env)
@@ -653,13 +699,11 @@ class Interp:
             return self.assign(obj_node, self.replace(cur, target.a[0], args, value), target_env, env)
         if k == "call" and target.a[0].kind == "name":
             fname = target.a[0].a[0] + "<-"
-            fn = self.builtins.get(fname)
-            if fn is None:
-                raise RError(f"could not find function \"{fname}\"")
+            fn = self.lookup_function(fname, env)
             obj_node = target.a[1][0][1]
             cur = self._current(obj_node, target_env, env)
             extra = [(a, self.eval(v, env)) for a, v in target.a[1][1:]]
-            return self.assign(obj_node, fn(self, [(None, cur)] + extra + [("value", value)], env), target_env, env)
+            return self.assign(obj_node, self.apply(fn, [(None, cur)] + extra + [("value", value)], env), target_env, env)
         raise RError("invalid assignment target")
 
     def _current(self, node, target_env, env):

@@ -191,3 +191,107 @@ def test_kernel_mirror_against_the_executed_reference(oracle):
             assert r.max() < 1e-8, (case["name"], r)
         n += 1
     assert n == 7
+
+
+API_CASES = [c for c in CASES if "api" in c]
+
+
+@pytest.mark.parametrize("case", API_CASES, ids=[c["name"] for c in API_CASES])
+def test_oracle_pipeline_reproduces_the_executed_run_lineagepulse(oracle, case):
+    """runLineagePulse (main_LineagePulse.R:219-328) executed from the reference's text -- processSCData's filters,
+    calcNormConst, fitLPModels' fits A-D in either noise-model order, runDEAnalysis' table -- against the oracle pipeline
+    the GPU tests and bench.py compare with: log-likelihood columns, mean_H0 and the EM trajectories to the last bit,
+    p-values at 1e-10 (R's pchisq is restated twice, by mpmath there and in C here), the NA row of the all-zero gene."""
+    d, how, api = case["data"], case["how"], case["api"]
+    res = api["dfResults"]
+    all_genes = [f"gene_{i + 1}" for i in range(len(d["counts"]))]
+    all_cells = [f"cell_{j + 1}" for j in range(len(d["t"]))]
+    gi = [all_genes.index(g) for g in api["genes_kept"]]
+    ci = [all_cells.index(c) for c in api["cells_kept"]]
+    counts = np.asarray(d["counts"])
+    assert gi == [i for i in range(len(all_genes)) if counts[i].sum() > 0]          # processSCData.R:285-289
+    assert ci == [j for j in range(len(all_cells)) if counts[:, j].sum() > 0]
+    X = np.ascontiguousarray(counts[np.ix_(gi, ci)], dtype=np.int32)
+    G, N = X.shape
+    t = np.asarray(d["t"], dtype=np.float64)[ci]
+    sf = np.asarray(d["sf"], dtype=np.float64)[ci]
+    batch = [d["batch"][j] for j in ci]
+    groups = [d["groups"][j] for j in ci]
+    h1_mu = how["strMuModel"]
+    h1_disp = how.get("strDispModelFull", "constant")
+    design = A.DesignData(
+        G, N, size_factors=sf, pseudotime=t, groups=groups if h1_mu == "groups" else None,
+        spline_basis_mu=ns(t, int(how["scaDFSplinesMu"])) if h1_mu == "splines" else None,
+        spline_basis_disp=ns(t, int(how["scaDFSplinesDisp"])) if h1_disp == "splines" else None,
+        impulse_basis=ns(t, 4), confounders_mu=[batch] if how.get("vecConfoundersMu") else None)
+    drop = how["strDropModel"]
+    m_h1, m_h0 = model(h1_mu, h1_disp, drop), model("constant", "constant", drop)
+    m_h1_nb, m_h0_nb = model(h1_mu, h1_disp), model("constant", "constant")
+    noise_on_h0 = how.get("boolEstimateNoiseBasedOnH0", True)
+    m_a, m_b = (m_h0, m_h1) if noise_on_h0 else (m_h1, m_h0)
+    p_a = A.ParamsData(design, m_a)
+    r_a = oracle.fit_model(X, design, m_a, p_a, True)
+    p_b = A.ParamsData(design, m_b)
+    p_b.mat_drop = p_a.mat_drop.copy(order="F")
+    oracle.fit_model(X, design, m_b, p_b, False)
+    p_h1, p_h0 = (p_b, p_a) if noise_on_h0 else (p_a, p_b)
+    p_h0_nb, p_h1_nb = A.ParamsData(design, m_h0_nb), A.ParamsData(design, m_h1_nb)
+    oracle.fit_model(X, design, m_h0_nb, p_h0_nb, False)
+    oracle.fit_model(X, design, m_h1_nb, p_h1_nb, False)
+    ll = {"loglik_full_zinb": oracle.eval_loglik(X, design, m_h1, p_h1), "loglik_red_zinb": oracle.eval_loglik(X, design, m_h0, p_h0),
+          "loglik_full_nb": oracle.eval_loglik(X, design, m_h1_nb, p_h1_nb), "loglik_red_nb": oracle.eval_loglik(X, design, m_h0_nb, p_h0_nb)}
+    rows = [api["row_names"].index(g) for g in api["genes_kept"]]
+    col = lambda name: np.array([res[name][r] for r in rows], dtype=np.float64)     # noqa: E731
+    for name, v in ll.items():      # lm() ran in the oracle's operation order: the impulse run is exact as well
+        assert np.array_equal(v, col(name)), name
+    em_a = api["vecEMLogLikH0"] if noise_on_h0 else api["vecEMLogLikH1"]
+    assert np.array_equal(r_a["em_ll"][: r_a["n_iter"]], np.asarray(em_a))
+    assert np.array_equal(p_h0_nb.mat_mu[:, 0], col("mean_H0"))                    # runHypothesisTests.R:99-103
+    ddf = design.deg_freedom(m_h1) - design.deg_freedom(m_h0)
+    assert np.all(col("df_full_zinb") == design.deg_freedom(m_h1)) and np.all(col("df_red_zinb") == design.deg_freedom(m_h0))
+    assert np.all(col("df_full_nb") == design.deg_freedom(m_h1)) and np.all(col("df_red_nb") == design.deg_freedom(m_h0))
+    p, padj = oracle.lrt(ll["loglik_full_zinb"], ll["loglik_red_zinb"], ddf)
+    _, padj_nb = oracle.lrt(ll["loglik_full_nb"], ll["loglik_red_nb"], ddf)
+    assert np.max(rel(p, col("p"))) < 1e-10 and np.max(rel(padj, col("padj"))) < 1e-10
+    assert np.array_equal(col("p_nb"), col("p"))                                   # the reference's quirk (:110): p_nb = p
+    assert np.max(rel(padj_nb, col("padj_nb"))) < 1e-10
+    # rows of filtered genes: all NA, allZero TRUE; the table is in the order of the input genes
+    assert api["row_names"] == all_genes
+    for r, g in enumerate(all_genes):
+        assert res["allZero"][r] == (g not in api["genes_kept"])
+        if g not in api["genes_kept"]:
+            assert res["p"][r] is None and res["loglik_full_zinb"][r] is None and res["gene"][r] is None
+
+
+def test_product_host_layer_against_the_executed_reference():
+    """The host side of the product that runs without a GPU -- processSCData's filters and report, the LRT arithmetic
+    of lpb200_lrt -- on the inputs and outputs of the executed runLineagePulse."""
+    import lineagepulse_b200 as lp
+    from lineagepulse_b200.engine import lrt
+    for case in API_CASES:
+        d, how, api = case["data"], case["how"], case["api"]
+        X = np.asarray(d["counts"], dtype=np.float64)
+        cells = [f"cell_{j + 1}" for j in range(X.shape[1])]
+        genes = [f"gene_{i + 1}" for i in range(X.shape[0])]
+        sf = dict(zip(cells, d["sf"]))
+        r = lp.processSCData(X, {"cell": cells, "continuous": d["t"], "groups": d["groups"], "batch": d["batch"]},
+                             strMuModel=how["strMuModel"], vecConfoundersMu=how.get("vecConfoundersMu"),
+                             strDispModelFull=how.get("strDispModelFull", "constant"), scaDFSplinesMu=how.get("scaDFSplinesMu", 6),
+                             scaDFSplinesDisp=how.get("scaDFSplinesDisp", 3), vecNormConstExternal=sf, boolVerbose=False,
+                             rownames=genes, colnames=cells)
+        obj = r["objLP"]
+        ref_lines = api["strReport"].split("\n")
+        got_lines = obj.strReport.split("\n")
+        n = len([ln for ln in got_lines if ln])
+        assert n >= 4 and got_lines[1:n] == ref_lines[1:n], (got_lines[:n], ref_lines[:n])   # line 0 carries the version
+        assert list(obj.vecAllGenes) == genes
+        assert list(np.asarray(obj.dfAnnotationProc["cell"])) == api["cells_kept"]
+        assert [float(r["vecNormConstExternalProc"][k]) for k in range(len(api["cells_kept"]))] == [sf[c] for c in api["cells_kept"]]
+        res = api["dfResults"]
+        rows = [api["row_names"].index(g) for g in api["genes_kept"]]
+        col = lambda name: np.array([res[name][k] for k in rows], dtype=np.float64)     # noqa: E731
+        ddf = int(res["df_full_zinb"][rows[0]] - res["df_red_zinb"][rows[0]])
+        p, padj = lrt(col("loglik_full_zinb"), col("loglik_red_zinb"), ddf)
+        assert np.max(rel(p, col("p"))) < 1e-10 and np.max(rel(padj, col("padj"))) < 1e-10
+        _, padj_nb = lrt(col("loglik_full_nb"), col("loglik_red_nb"), ddf)
+        assert np.max(rel(padj_nb, col("padj_nb"))) < 1e-10
