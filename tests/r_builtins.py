@@ -400,7 +400,7 @@ def install(I):
             return B["names"](I, [(None, x)], env)
         if which == "dim":
             return B["dim"](I, [(None, x)], env)
-        return x.attrs.get(which) if isinstance(x, RList) else None
+        return (x.attrs or {}).get(which)
 
     @reg("unlist")
     def _(I, args, env):
@@ -886,5 +886,26 @@ def install(I):
         out.attrs = {"class": "data.frame", "row.names": [str(k + 1) for k in range(n)]}
         return out
 
-    B["attr<-"] = lambda I, a, e: a[0][1]
+    @reg("attr<-")
+    def _(I, args, env):
+        x, which, value = args[0][1], args[1][1].v[0], args[-1][1]
+        if isinstance(x, RList):
+            out = RList(x.v, x.names)
+            out.attrs = dict(x.attrs)
+            out.attrs[which] = value
+            return out
+        attrs = dict(x.attrs or {})
+        attrs[which] = value
+        return RVec(x.v, names=x.names, dim=x.dim, dimnames=x.dimnames, attrs=attrs)
+
+    from tests.r_eval import Env
+    B["new.env"] = lambda I, a, e: Env(None)
+    B["emptyenv"] = lambda I, a, e: None
+    B["getOption"] = lambda I, a, e: a[1][1] if len(a) > 1 else None
+
+    @reg(".Call")
+    def _(I, args, env):
+        if getattr(I, "dot_call", None) is None:
+            raise RError(".Call: no native routines are loaded")
+        return I.dot_call(args[0][1].v[0], [v for _, v in args[1:]])
     B["invisible"] = lambda I, a, e: a[0][1] if a else None

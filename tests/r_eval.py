@@ -36,9 +36,10 @@ class _Next(Exception):
 class RVec:
     """Atomic vector: v is a 1-D numpy array (float64, int64, bool or object for character); matrices keep dim = (nr, nc)
     with column-major data."""
-    __slots__ = ("v", "names", "dim", "dimnames")
+    __slots__ = ("v", "names", "dim", "dimnames", "attrs")
 
-    def __init__(self, v, names=None, dim=None, dimnames=None):
+    def __init__(self, v, names=None, dim=None, dimnames=None, attrs=None):
+        self.attrs = attrs          # other attributes (attr(x, "name") <- value); dropped by subsetting and arithmetic
         self.v = np.atleast_1d(np.asarray(v))
         if self.v.dtype.kind in "US":
             self.v = self.v.astype(object)
@@ -309,6 +310,8 @@ class Interp:
                 return None
             if isinstance(obj, RList):
                 return obj.get(n.a[1], exact=False)
+            if isinstance(obj, Env):
+                return self.force(obj.vars.get(n.a[1]))
             raise RError("$ operator is invalid for atomic vectors")
         if k == "at":
             obj = self.eval(n.a[0], env)
@@ -678,6 +681,9 @@ class Interp:
         if k == "dollar":
             obj_node = target.a[0]
             cur = self._current(obj_node, target_env, env)
+            if isinstance(cur, Env):          # environments are reference objects: modified in place
+                cur.vars[target.a[1]] = value
+                return
             if cur is None:
                 cur = RList()
             if not isinstance(cur, RList):

@@ -295,3 +295,90 @@ def test_product_host_layer_against_the_executed_reference():
         assert np.max(rel(p, col("p"))) < 1e-10 and np.max(rel(padj, col("padj"))) < 1e-10
         _, padj_nb = lrt(col("loglik_full_nb"), col("loglik_red_nb"), ddf)
         assert np.max(rel(padj_nb, col("padj_nb"))) < 1e-10
+
+
+@pytest.mark.skipif(not glob.glob("/root/reference/R/*.R"), reason="the reference's sources exist in the build container only")
+def test_r_wrappers_executed_inside_the_reference_s_run_lineagepulse(oracle):
+    """r_shim/R/lpb200_wrappers.R EXECUTED: the reference's R files are loaded into the evaluator, then the wrapper file
+    on top of them (its fitLPModels / fitModel / fitMuDisp / fitPi / evalLogLikMatrix replace the reference's), and the
+    reference's own runLineagePulse is called.  .Call() is answered by tests/r_shim_mock.py: lp_rshim.c's argument and
+    result conventions over the CPU oracle.  The results table must equal the one the unmodified reference produced
+    (tests/golden/reference_exec.json) -- every line of lpAttachCounts, lpContext, lpSetDesign, lpDesign, lpModel,
+    lpParams, lpControl, lpSplitBatch, fitModel, fitModelsConcurrently and fitLPModels runs on the way."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_exec_golden as gen
+    from tests.r_shim_mock import ShimMock
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = gen.Reference("/root/reference", dnbinom=lambda x, s, mu: oracle.dnbinom_mu_log(x, s, mu))
+    ref.I.lm_solver = gen.lm_in_the_oracle_s_order
+    ref.I.load(open(os.path.join(root, "r_shim", "R", "lpb200_wrappers.R")).read(), only_definitions=False)
+    mock = ShimMock(oracle)
+    ref.I.dot_call = mock
+    for case in API_CASES:
+        mock.calls.clear()
+        data = {k: np.asarray(v) for k, v in case["data"].items()}
+        out = gen.run_lineagepulse(ref, data, **case["how"])
+        want = case["api"]
+        assert out["row_names"] == want["row_names"] and out["genes_kept"] == want["genes_kept"]
+        for name in ("loglik_full_zinb", "loglik_red_zinb", "loglik_full_nb", "loglik_red_nb", "mean_H0", "p", "padj", "p_nb",
+                     "padj_nb", "df_full_zinb", "df_red_zinb", "df_full_nb", "df_red_nb", "allZero", "gene"):
+            assert out["dfResults"][name] == want["dfResults"][name], (case["name"], name)
+        noise_on_h0 = case["how"].get("boolEstimateNoiseBasedOnH0", True)
+        key = "vecEMLogLikH0" if noise_on_h0 else "vecEMLogLikH1"
+        assert out[key] == want[key], case["name"]
+        # one context and one upload per run, the whole EM and the three other fits in one call each, four likelihood
+        # evaluations for the table; the design is re-sent only when it changes (H0 <-> H1 covariates)
+        assert mock.calls.count("lp_create") == 1 and mock.calls.count("lp_load_counts_dense") == 1
+        assert mock.calls.count("lp_fit_model") == 1 and mock.calls.count("lp_fit_models") == 1
+        assert mock.calls.count("lp_eval_loglik") == 4 and mock.calls.count("lp_set_control") == 2
+        assert 2 <= mock.calls.count("lp_set_design") <= 6, mock.calls
+
+
+@pytest.mark.skipif(not glob.glob("/root/reference/R/*.R"), reason="the reference's sources exist in the build container only")
+def test_r_wrappers_under_the_reference_s_own_em_loop(oracle):
+    """The other integration INTEGRATION.md offers: fitModel and fitLPModels stay the reference's R code (its EM loop, its
+    sequence of fits) and only the L2 functions -- fitMuDisp, fitPi, evalLogLikMatrix -- are the wrappers.  Executed as
+    above; the table must again equal the unmodified reference's.  lpLRT is called directly."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_exec_golden as gen
+    from tests import r_parse
+    from tests.r_eval import RVec
+    from tests.r_shim_mock import ShimMock
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = gen.Reference("/root/reference", dnbinom=lambda x, s, mu: oracle.dnbinom_mu_log(x, s, mu))
+    ref.I.lm_solver = gen.lm_in_the_oracle_s_order
+    keep = {name: ref.I.globals.vars[name] for name in ("fitModel", "fitLPModels")}
+    ref.I.load(open(os.path.join(root, "r_shim", "R", "lpb200_wrappers.R")).read(), only_definitions=False)
+    ref.I.globals.vars.update(keep)
+    # the one line INTEGRATION.md asks the maintainer to add to processSCData: attach the count matrix to its GPU context
+    ref.I.load("""
+processSCData_reference <- processSCData
+processSCData <- function(...) {
+    lsProcessed <- processSCData_reference(...)
+    lsProcessed$objLP@matCountsProc <- lpAttachCounts(lsProcessed$objLP@matCountsProc)
+    lsProcessed
+}
+""", only_definitions=False)
+    mock = ShimMock(oracle)
+    ref.I.dot_call = mock
+    for case in API_CASES:
+        if "impulse" in case["name"]:
+            continue
+        mock.calls.clear()
+        data = {k: np.asarray(v) for k, v in case["data"].items()}
+        out = gen.run_lineagepulse(ref, data, **case["how"])
+        want = case["api"]
+        for name in ("loglik_full_zinb", "loglik_red_zinb", "loglik_full_nb", "loglik_red_nb", "mean_H0", "p", "padj", "padj_nb", "gene"):
+            assert out["dfResults"][name] == want["dfResults"][name], (case["name"], name)
+        assert out["vecEMLogLikH0"] == want["vecEMLogLikH0"] and out["vecEMLogLikH1"] == want["vecEMLogLikH1"]
+        n_cycles = len(want["vecEMLogLikH0" if case["how"].get("boolEstimateNoiseBasedOnH0", True) else "vecEMLogLikH1"])
+        assert mock.calls.count("lp_fit_pi") == n_cycles and mock.calls.count("lp_fit_mudisp") == n_cycles + 3
+        assert mock.calls.count("lp_fit_model") == 0 and mock.calls.count("lp_fit_models") == 0
+        # the context travels with the matrix: one upload although every L2 call receives the matrix anew
+        assert mock.calls.count("lp_create") == 1 and mock.calls.count("lp_load_counts_dense") == 1, mock.calls
+    res = ref.call("lpLRT", vecLogLikFull=RVec(np.array([-100.0, -50.0, -70.0])), vecLogLikRed=RVec(np.array([-104.0, -50.5, -90.0])),
+                   scaDeltaDegFreedom=RVec(np.array([3.0])))
+    p, padj = oracle.lrt(np.array([-100.0, -50.0, -70.0]), np.array([-104.0, -50.5, -90.0]), 3)
+    assert res.names == ["p", "padj"] and np.array_equal(res.v[0].v, p) and np.array_equal(res.v[1].v, padj)
