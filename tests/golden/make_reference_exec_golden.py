@@ -121,6 +121,16 @@ def make_data(seed, G=9, N=26, size_factors=False):
     return dict(counts=X, t=t, groups=groups, batch=batch, sf=sf)
 
 
+def data_json(data):
+    """The inputs as stored in the JSON, with the natural-spline bases the run used (splines::ns restated in
+    lineagepulse_b200/splines.py goes through LAPACK's QR, whose last bits depend on the BLAS kernels of the machine: the
+    tests feed the oracle these stored bases, so the stored outputs do not depend on the BLAS of the test machine)."""
+    from lineagepulse_b200.splines import ns
+    out = {k: np.asarray(v).tolist() for k, v in data.items()}
+    out["ns"] = {str(df): ns(np.asarray(data["t"], dtype=np.float64), df).tolist() for df in (3, 4)}
+    return out
+
+
 def r_inputs(data):
     X = data["counts"].astype(np.float64)
     G, N = X.shape
@@ -215,6 +225,31 @@ def objective_vectors(ref, data, res, rng, n_random=6):
     return out
 
 
+def reexecute(case, cases, root="/root/reference"):
+    """Runs ONE fit case of the JSON again, now, on this machine: the reference's fitModel from its source text on the
+    stored inputs (a case that was fitted given another case's drop-out model -- `given` -- runs that case first).  For
+    tests/test_reference_exec.py on a machine whose C library rounds exp / log differently from the one the JSON was made
+    on: the stored bits are then not this machine's, the comparison to the last bit is made against this run instead."""
+    from tests.oracle_binding import Oracle
+    orc = Oracle()
+    ref = Reference(root, dnbinom=lambda x, s, m: orc.dnbinom_mu_log(x, s, m))
+    ref.I.lm_solver = lm_in_the_oracle_s_order
+
+    def run(c):
+        d = c["data"]
+        data = dict(counts=np.asarray(d["counts"], dtype=np.int64), t=np.asarray(d["t"], dtype=np.float64),
+                    groups=np.asarray(d["groups"]), batch=np.asarray(d["batch"]), sf=np.asarray(d["sf"], dtype=np.float64))
+        how = {k: v for k, v in c["how"].items() if k != "matDropoutLinModel"}
+        drop = None
+        if c.get("given"):    # that case's lsDropModel list, holding the STORED matrix (what the oracle is handed, too)
+            drop = run(next(x for x in cases if x["name"] == c["given"]))[0].get("lsDropModel")
+            m = drop.get("matDropoutLinModel")
+            m.v = np.asarray(c["how"]["matDropoutLinModel"], dtype=np.float64).reshape(m.dim).reshape(-1, order="F")
+        return fit_model(ref, data, lsDropModel=drop, **how)
+
+    return run(case)[1]
+
+
 def main():
     root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     from tests.oracle_binding import Oracle
@@ -224,9 +259,11 @@ def main():
     rng = np.random.default_rng(2024)
     cases = []
 
-    def add(name, data, how, res_out, objective=None):
+    def add(name, data, how, res_out, objective=None, given=None):
         res, out = res_out
-        case = dict(name=name, how=how, data={k: np.asarray(v).tolist() for k, v in data.items()}, reference=out)
+        case = dict(name=name, how=how, data=data_json(data), reference=out)
+        if given is not None:
+            case["given"] = given         # the case whose fitted drop-out model this fit was handed (lsDropModel)
         if objective is not None:
             case["objective"] = objective
         cases.append(case)
@@ -248,7 +285,8 @@ def main():
         how = dict(strMuModel="impulse", strDispModel="constant", strDropModel="logistic")
         r = fit_model(fast, d1, lsDropModel=dropA, **how)
         add(f"H1 impulse ZINB given fit A's drop-out model (fit B), {tag}", d1, dict(how, matDropoutLinModel=dropA_py), r,
-            objective_vectors(exact, d1, r[0], rng, n_random=3) if solver is numpy_lm else None)
+            objective_vectors(exact, d1, r[0], rng, n_random=3) if solver is numpy_lm else None,
+            given="H0 constant ZINB, drop-out EM (fit A)")
         how = dict(strMuModel="impulse", strDispModel="constant", strDropModel="none")
         r = fit_model(fast, d1, **how)
         add(f"impulse NB (fit D), {tag}", d1, how, r)
@@ -268,7 +306,7 @@ def main():
         starts.append(dict(peak=as_py(st.get("peak")), valley=as_py(st.get("valley"))))
     cases.append(dict(name="initialiseImpulseParameters (lm by numpy QR)", how=dict(strMuModel="impulse", strDispModel="constant",
                                                                                       strDropModel="none"),
-                      data={k: np.asarray(v).tolist() for k, v in d1.items()}, starts=starts))
+                      data=data_json(d1), starts=starts))
     fast.I.lm_solver = lm_in_the_oracle_s_order
 
     d2 = make_data(12, size_factors=True)
@@ -280,11 +318,11 @@ def main():
     how = dict(strMuModel="groups", strDispModel="constant", strDropModel="logistic", vecConfoundersMu=["batch"])
     r = fit_model(fast, d2, lsDropModel=drop2, **how)
     add("groups + batch confounder ZINB (C4 shape), size factors", d2, dict(how, matDropoutLinModel=drop2_py), r,
-        objective_vectors(exact, d2, r[0], rng, n_random=3))
+        objective_vectors(exact, d2, r[0], rng, n_random=3), given="H0 constant ZINB with size factors, drop-out EM")
     how = dict(strMuModel="splines", strDispModel="constant", strDropModel="logistic", scaDFSplinesMu=4)
     r = fit_model(fast, d2, lsDropModel=drop2, **how)
     add("splines (df 4) ZINB (C5 shape), size factors", d2, dict(how, matDropoutLinModel=drop2_py), r,
-        objective_vectors(exact, d2, r[0], rng, n_random=3))
+        objective_vectors(exact, d2, r[0], rng, n_random=3), given="H0 constant ZINB with size factors, drop-out EM")
     how = dict(strMuModel="constant", strDispModel="groups", strDropModel="none", vecConfoundersDisp=["batch"])
     r = fit_model(fast, d2, **how)
     add("dispersion groups + dispersion batch confounder, NB", d2, how, r, objective_vectors(exact, d2, r[0], rng, n_random=3))
@@ -313,7 +351,7 @@ def main():
                      ("splines with dispersion splines under H1", dict(strMuModel="splines", scaDFSplinesMu=4, strDispModelFull="splines",
                                                                        scaDFSplinesDisp=3, strDropModel="logistic"))):
         out = run_lineagepulse(fast, d4, **kw)
-        cases.append(dict(name="runLineagePulse: " + name, how=kw, data={k: np.asarray(v).tolist() for k, v in d4.items()}, api=out))
+        cases.append(dict(name="runLineagePulse: " + name, how=kw, data=data_json(d4), api=out))
         print("runLineagePulse:", name, out["seconds"], "s; p =", out["dfResults"]["p"][:3], flush=True)
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_exec.json")
