@@ -513,7 +513,10 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
             raise LineagePulseError("ERROR IN INPUT DATA: Input matrix file is not .mtx. "
                                     "Supply counts as .mtx file or as R matrix object.")
         import scipy.io
-        counts = scipy.io.mmread(counts).tocsc()
+        try:
+            counts = sp.csc_matrix(scipy.io.mmread(counts, spmatrix=True))
+        except TypeError:      # scipy without the spmatrix switch
+            counts = sp.csc_matrix(scipy.io.mmread(counts))
     if counts is None:
         raise LineagePulseError("ERROR: counts was not given as input.")
     if dfAnnotation is None:

@@ -130,6 +130,37 @@ def test_process_sc_data_filters_and_errors():
         lp.processSCData(X, annot, vecConfoundersMu=["batch"], strMuModel="constant", boolVerbose=False)
 
 
+def test_process_sc_data_mtx_and_sparse_ingest(tmp_path):
+    """processSCData.R:102-112: counts given as a MatrixMarket file name (readMM), as a sparse matrix or as a dense one
+    lead to the same processed matrix, annotation and report; any other file name is the reference's error."""
+    import scipy.io
+    import scipy.sparse as sp
+    rng = np.random.default_rng(4)
+    X = rng.poisson(0.6, size=(7, 9)).astype(np.int64)
+    X[2, :] = 0                        # an all-zero gene
+    X[:, 4] = 0                        # an all-zero cell
+    cells = np.array([f"c{j}" for j in range(9)])
+    genes = [f"g{i}" for i in range(7)]
+    t = np.linspace(0.0, 1.0, 9)
+    t[7] = np.nan                      # a cell without pseudotime
+    annot = {"cell": cells, "continuous": t}
+    path = str(tmp_path / "counts.mtx")
+    scipy.io.mmwrite(path, sp.csc_matrix(X))
+    kw = dict(strMuModel="splines", scaDFSplinesMu=3, boolVerbose=False, rownames=genes, colnames=cells)
+    objs = [lp.processSCData(src, annot, **kw)["objLP"] for src in (path, sp.csc_matrix(X), X.astype(float), X.astype(np.int32))]
+    keep_g = [i for i in range(7) if i != 2 and X[i, [j for j in range(9) if j not in (4, 7)]].sum() > 0]
+    keep_c = [j for j in range(9) if j not in (4, 7) and X[:, j].sum() > 0]
+    want = X[np.ix_(keep_g, keep_c)]
+    for obj in objs:
+        assert np.array_equal(obj.matCountsProc.dense(), want)
+        assert list(obj.matCountsProc.rownames) == [genes[i] for i in keep_g]
+        assert list(obj.matCountsProc.colnames) == [cells[j] for j in keep_c]
+        assert list(obj.vecAllGenes) == genes
+        assert obj.strReport.split("\n")[1:] == objs[0].strReport.split("\n")[1:]
+    with pytest.raises(lp.LineagePulseError, match="Input matrix file is not .mtx"):
+        lp.processSCData(str(tmp_path / "counts.csv"), annot, **kw)
+
+
 def test_object_accessors():
     obj = lp.LineagePulseObject(strReport="x", vecAllGenes=np.array(["g"]))
     assert "dfResults" in obj.names() and obj["strReport"] == "x"
