@@ -577,6 +577,24 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
             matPiConstPredictors = matPiConstPredictors.reshape(-1, 1)
         if matPiConstPredictors.shape[0] != G:
             raise LineagePulseError("ERROR: Some genes named in rows of counts do not occur in rows of matPiConstPredictors.")
+    mperm = None
+    if len(cells) == N and not np.array_equal(colnames, cells):
+        # processSCData.R:255-258 sorts the COUNT columns by match(colnames(counts), dfAnnotation$cell): column k of the sorted
+        # matrix is the old column at the annotation position of the k-th column name.  That is the INVERSE of the permutation
+        # that lines the columns up with the annotation; the two agree only for permutations that are their
+        # own inverse (e.g. one swap).  Reproduced as it is: everything downstream pairs count columns and annotation rows by
+        # position, size factors by column name (:292).
+        pos = {c: k for k, c in enumerate(cells)}
+        mperm = np.array([pos[c] for c in colnames])
+        counts = counts.tocsc()[:, mperm] if sparse else np.ascontiguousarray(np.asarray(counts)[:, mperm])
+        colnames = colnames[mperm]
+        if vecNormConstExternal is not None and not isinstance(vecNormConstExternal, dict):
+            vecNormConstExternal = np.asarray(vecNormConstExternal, dtype=np.float64)[mperm]   # positional: travels with its column
+        if not np.array_equal(colnames, cells):
+            warnings.warn("processSCData: the columns of counts were sorted as the reference sorts them (match(colnames(counts), "
+                          "dfAnnotation$cell), processSCData.R:255-258), which does not line them up with dfAnnotation for this "
+                          "order of cells; annotation rows and count columns are paired by position from here on, as in the "
+                          "reference. Supply counts and dfAnnotation in the same order of cells.")
     if isinstance(vecNormConstExternal, dict):
         # R's named vector (processSCData.R:215-221, :292): looked up by the cell names of the count matrix
         if not all(c in vecNormConstExternal for c in colnames):
@@ -587,8 +605,9 @@ def processSCData(counts, dfAnnotation, vecConfoundersDisp=None, vecConfoundersM
     if rownames is None:
         rownames = np.array([f"Gene_{i + 1}" for i in range(G)])
     rownames = np.asarray(rownames)
-    # order the annotation like the count columns (processSCData.R:255-258)
-    if not np.array_equal(colnames, cells):
+    # an annotation with MORE rows than counts has columns (the reference fails on it, subscript out of bounds): the rows of the
+    # cells of counts, in the order of the count columns
+    if mperm is None and not np.array_equal(colnames, cells):
         pos = {c: k for k, c in enumerate(cells)}
         order = np.array([pos[c] for c in colnames])
         dfAnnotation = {k: v[order] for k, v in dfAnnotation.items()}

@@ -161,6 +161,40 @@ def test_process_sc_data_mtx_and_sparse_ingest(tmp_path):
         lp.processSCData(str(tmp_path / "counts.csv"), annot, **kw)
 
 
+def test_process_sc_data_column_order_is_the_executed_reference_s():
+    """processSCData.R:255-258 on counts whose columns are ordered differently from dfAnnotation$cell: the reference sorts the
+    count columns by match(colnames(counts), dfAnnotation$cell) -- the inverse of the lining-up permutation
+    -- and pairs by position afterwards, size factors by column name.  tests/golden/process_sc_data_order.json holds what the
+    reference's own text returns (executed by tests/r_eval.py, make_process_order_golden.py): swaps line up, cycles do not,
+    and the product returns the same object either way -- with a warning where the names no longer line up."""
+    import json
+    import warnings as W
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "process_sc_data_order.json")))["cases"]
+    assert len(cases) == 6
+    for case in cases:
+        ref = case["reference"]
+        X = np.asarray(case["counts"], dtype=np.int64)
+        t = np.array([np.nan if v is None else v for v in case["t"]])
+        annot = {"cell": np.array(case["cells"]), "continuous": t}
+        sf = dict(zip(case["cells"], case["sf"]))
+        lined_up = ref["colnames"] == ref["annotation_cell"]
+        assert lined_up == (case["name"] in ("same order", "one swap", "two swaps", "reversed"))
+        for counts in (X.astype(float), X.astype(np.int32)):
+            with W.catch_warnings(record=True) as caught:
+                W.simplefilter("always")
+                r = lp.processSCData(counts, annot, strMuModel="splines", scaDFSplinesMu=3, vecNormConstExternal=sf,
+                                     boolVerbose=False, rownames=case["genes"], colnames=case["colnames"])
+            assert any("processSCData.R:255-258" in str(w.message) for w in caught) == (not lined_up), case["name"]
+            obj = r["objLP"]
+            assert list(obj.matCountsProc.colnames) == ref["colnames"], case["name"]
+            assert list(obj.matCountsProc.rownames) == ref["rownames"]
+            assert np.array_equal(obj.matCountsProc.dense(), np.asarray(ref["counts"])), case["name"]
+            assert list(obj.dfAnnotationProc["cell"]) == ref["annotation_cell"]
+            assert list(obj.dfAnnotationProc["continuous"]) == ref["annotation_continuous"]
+            assert list(r["vecNormConstExternalProc"]) == ref["vecNormConstExternalProc"], case["name"]
+            assert obj.strReport.split("\n")[1:4] == ref["report"][:3]
+
+
 def test_object_accessors():
     obj = lp.LineagePulseObject(strReport="x", vecAllGenes=np.array(["g"]))
     assert "dfResults" in obj.names() and obj["strReport"] == "x"
