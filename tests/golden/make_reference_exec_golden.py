@@ -245,7 +245,12 @@ def reexecute(case, cases, root="/root/reference"):
             drop = run(next(x for x in cases if x["name"] == c["given"]))[0].get("lsDropModel")
             m = drop.get("matDropoutLinModel")
             m.v = np.asarray(c["how"]["matDropoutLinModel"], dtype=np.float64).reshape(m.dim).reshape(-1, order="F")
-        return fit_model(ref, data, lsDropModel=drop, **how)
+        pred = None
+        if "pi_const_pred" in d:
+            pm = np.asarray(d["pi_const_pred"], dtype=np.float64)
+            pred = RVec(pm.reshape(-1, order="F"), dim=pm.shape,
+                        dimnames=([f"gene_{i + 1}" for i in range(pm.shape[0])], [f"p{k + 1}" for k in range(pm.shape[1])]))
+        return fit_model(ref, data, lsDropModel=drop, matPiConstPredictors=pred, **how)
 
     return run(case)[1]
 
@@ -337,6 +342,38 @@ def main():
     how = dict(strMuModel="constant", strDispModel="constant", strDropModel="logistic", strDropFitGroup="ForAllCells")
     r = fit_model(fast, d3, **how)
     add("H0 constant ZINB, ForAllCells drop-out EM", d3, how, r)
+
+    # gene-wise drop-out predictors (matPiConstPredictors: decompressDropoutRateByCell / ByGene with constant predictors,
+    # fitPi's parameter layout with them, fitDropout.R:59-140)
+    pred = np.round(np.random.default_rng(5).normal(0, 1, (d3["counts"].shape[0], 2)), 3)
+    genes3 = [f"gene_{i + 1}" for i in range(pred.shape[0])]
+    for drop, grp in (("logistic", "PerCell"), ("logistic_ofMu", "PerCell"), ("logistic_ofMu", "ForAllCells")):
+        how = dict(strMuModel="constant", strDispModel="constant", strDropModel=drop, strDropFitGroup=grp)
+        r = fit_model(fast, d3, matPiConstPredictors=RVec(pred.reshape(-1, order="F"), dim=pred.shape, dimnames=(genes3, ["p1", "p2"])), **how)
+        add(f"H0 constant ZINB, {drop} drop-out EM ({grp}) with two gene-wise predictors", dict(d3, pi_const_pred=pred), how, r)
+
+    # H1 fits GIVEN a logistic_ofMu drop-out model: the drop-out rate of every observation moves with the gene's mean
+    # parameters inside the fit (fitMeanDispersion.R:887-892 and evalLogLikMuDispGeneFit's vecPiParam path)
+    how = dict(strMuModel="constant", strDispModel="constant", strDropModel="logistic_ofMu")
+    fitA3 = fit_model(fast, d3, **how)[0]
+    drop3 = fitA3.get("lsDropModel")
+    drop3_py = as_py(drop3.get("matDropoutLinModel"))
+    for how in (dict(strMuModel="groups", strDispModel="constant", strDropModel="logistic_ofMu"),
+                dict(strMuModel="splines", strDispModel="groups", strDropModel="logistic_ofMu", scaDFSplinesMu=3),
+                dict(strMuModel="groups", strDispModel="splines", strDropModel="logistic_ofMu", scaDFSplinesDisp=3, vecConfoundersMu=["batch"])):
+        r = fit_model(fast, d3, lsDropModel=drop3, **how)
+        add(f"{how['strMuModel']} mean, {how['strDispModel']} dispersion ZINB given a logistic_ofMu drop-out model", d3,
+            dict(how, matDropoutLinModel=drop3_py), r, given="H0 constant ZINB, logistic_ofMu drop-out EM")
+
+    # two confounders each for the mean and the dispersion (lsmatBatchModel with two matrices; the annotation's group column
+    # serves as the second confounder): order of the batch parameters in the parameter vector, first level fixed at 1
+    how = dict(strMuModel="splines", strDispModel="constant", strDropModel="none", scaDFSplinesMu=3, vecConfoundersMu=["batch", "groups"])
+    r = fit_model(fast, d2, **how)
+    add("splines (df 3) with two mean confounders, NB, size factors", d2, how, r)
+    how = dict(strMuModel="constant", strDispModel="constant", strDropModel="none", vecConfoundersMu=["batch", "groups"],
+               vecConfoundersDisp=["groups", "batch"])
+    r = fit_model(fast, d2, **how)
+    add("constant with two mean and two dispersion confounders, NB, size factors", d2, how, r)
 
     # the public API end to end
     d4 = make_data(21, G=8, N=24, size_factors=True)

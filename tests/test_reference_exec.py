@@ -35,8 +35,9 @@ def _design(case):
         G, N, size_factors=None if np.all(sf == 1.0) else sf, pseudotime=t, groups=groups,
         spline_basis_mu=basis(how["scaDFSplinesMu"]) if how["strMuModel"] == "splines" else None,
         spline_basis_disp=basis(how["scaDFSplinesDisp"]) if how["strDispModel"] == "splines" else None,
-        impulse_basis=basis(4), confounders_mu=[d["batch"]] if how.get("vecConfoundersMu") else None,
-        confounders_disp=[d["batch"]] if how.get("vecConfoundersDisp") else None)
+        impulse_basis=basis(4), confounders_mu=[d[c] for c in how["vecConfoundersMu"]] if how.get("vecConfoundersMu") else None,
+        confounders_disp=[d[c] for c in how["vecConfoundersDisp"]] if how.get("vecConfoundersDisp") else None,
+        pi_const_pred=np.asarray(d["pi_const_pred"], dtype=np.float64) if "pi_const_pred" in d else None)
     m = model(how["strMuModel"], how["strDispModel"], how["strDropModel"], how.get("strDropFitGroup", "PerCell"))
     return X, design, m
 
@@ -92,10 +93,10 @@ def test_oracle_reproduces_the_executed_reference(oracle, case):
                      ("vecLL", ll, np.asarray(ref["vecLL"])), ("vecEMLogLikModel", r["em_ll"][: len(em)], em),
                      ("matMuModel", p.mat_mu, np.asarray(ref["matMuModel"], dtype=np.float64).reshape(p.mat_mu.shape)),
                      ("matDispModel", p.mat_disp, np.asarray(ref["matDispModel"], dtype=np.float64).reshape(p.mat_disp.shape))]
-            if ref["lsmatBatchModelMu"]:
-                pairs.append(("lsmatBatchModelMu", p.batch_mu[0], np.asarray(ref["lsmatBatchModelMu"][0])))
-            if ref["lsmatBatchModelDisp"]:
-                pairs.append(("lsmatBatchModelDisp", p.batch_disp[0], np.asarray(ref["lsmatBatchModelDisp"][0])))
+            for k, bm in enumerate(ref["lsmatBatchModelMu"] or []):
+                pairs.append((f"lsmatBatchModelMu[{k}]", p.batch_mu[k], np.asarray(bm)))
+            for k, bm in enumerate(ref["lsmatBatchModelDisp"] or []):
+                pairs.append((f"lsmatBatchModelDisp[{k}]", p.batch_disp[k], np.asarray(bm)))
             if ref["matDropoutLinModel"] is not None and "matDropoutLinModel" not in case["how"]:
                 pairs.append(("matDropoutLinModel", p.mat_drop,
                               np.asarray(ref["matDropoutLinModel"], dtype=np.float64).reshape(p.mat_drop.shape)))
@@ -264,7 +265,7 @@ def test_kernel_mirror_against_the_executed_reference(oracle):
         else:
             assert r.max() < 1e-8, (case["name"], r)
         n += 1
-    assert n == 7
+    assert n == 12     # fits B-D style cases: constant / impulse / groups / splines, one and two confounders, given drop-out models
 
 
 API_CASES = [c for c in CASES if "api" in c]
