@@ -470,3 +470,52 @@ processSCData <- function(...) {
                    scaDeltaDegFreedom=RVec(np.array([3.0])))
     p, padj = oracle.lrt(np.array([-100.0, -50.0, -70.0]), np.array([-104.0, -50.5, -90.0]), 3)
     assert res.names == ["p", "padj"] and np.array_equal(res.v[0].v, p) and np.array_equal(res.v[1].v, padj)
+
+
+@pytest.mark.skipif(not glob.glob("/root/reference/R/*.R"), reason="the reference's sources exist in the build container only")
+def test_warm_start_hooks_of_the_executed_reference(oracle):
+    """fitModel's warm-start hooks (fitModel.R:147-151; initialiseMuModel.R:93,131-133, initialiseDispModel.R) executed from
+    the reference's text: with matMuModelInit / matDispModelInit / lsmatBatchModelInitMu supplied and no drop-out model to
+    estimate, the reference's result is -- to the last bit -- fitMuDisp started from exactly those matrices (taken as stored:
+    means and batch factors on the natural scale).  That is the semantics lpb200_fit_model_from implements (keep_mask;
+    test_gpu_parity.py::test_warm_start_hooks asserts fit_model(keep) == fit_mudisp on the device)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_exec_golden as gen
+    from tests.r_eval import RList, RVec, as_py
+    ref = gen.Reference("/root/reference", dnbinom=lambda x, s, mu: oracle.dnbinom_mu_log(x, s, mu))
+    ref.I.lm_solver = gen.lm_in_the_oracle_s_order
+    d = gen.make_data(12, size_factors=True)
+    G, N = d["counts"].shape
+    t = np.asarray(d["t"], dtype=np.float64)
+    X = np.ascontiguousarray(d["counts"], dtype=np.int32)
+    mat, df, sf = gen.r_inputs(d)
+    genes = [f"gene_{i + 1}" for i in range(G)]
+    rng = np.random.default_rng(3)
+
+    def rmat(a):
+        return RVec(a.reshape(-1, order="F"), dim=a.shape, dimnames=(genes, None))
+
+    for mu_model, conf in (("constant", None), ("groups", ["batch"])):
+        design = A.DesignData(G, N, size_factors=np.asarray(d["sf"], dtype=np.float64), pseudotime=t,
+                              groups=d["groups"] if mu_model == "groups" else None, impulse_basis=ns(t, 4),
+                              confounders_mu=[d["batch"]] if conf else None)
+        m = model(mu_model, "constant", "none")
+        p = oracle.init_params(X, design, m)
+        p.mat_mu = np.asfortranarray(p.mat_mu * rng.uniform(0.5, 2.0, p.mat_mu.shape))
+        p.mat_disp = np.asfortranarray(rng.uniform(0.5, 3.0, p.mat_disp.shape))
+        kw = dict(matMuModelInit=rmat(p.mat_mu), matDispModelInit=rmat(p.mat_disp))
+        if conf:
+            p.batch_mu = [np.asfortranarray(np.column_stack([np.ones(G), rng.uniform(0.7, 1.5, (G, 2))]))]
+            kw["lsmatBatchModelInitMu"] = RList([rmat(p.batch_mu[0])])
+        res = ref.call("fitModel", matCounts=mat, dfAnnotation=df, vecConfoundersMu=None if conf is None else gen.S(conf),
+                       vecConfoundersDisp=None, vecNormConst=sf, scaDFSplinesMu=None, scaDFSplinesDisp=None, matWeights=None,
+                       matPiConstPredictors=None, lsDropModel=None, strMuModel=gen.S(mu_model), strDispModel=gen.S("constant"),
+                       strDropModel=gen.S("none"), strDropFitGroup=gen.S("PerCell"), scaMaxEstimationCycles=gen.D(20),
+                       boolVerbose=gen.B(False), boolSuperVerbose=gen.B(False), **kw)
+        oracle.fit_mudisp(X, design, m, p)
+        mu_ref = np.asarray(as_py(res.get("lsMuModel").get("matMuModel")), dtype=np.float64).reshape(p.mat_mu.shape)
+        disp_ref = np.asarray(as_py(res.get("lsDispModel").get("matDispModel")), dtype=np.float64).reshape(p.mat_disp.shape)
+        assert np.array_equal(p.mat_mu, mu_ref) and np.array_equal(p.mat_disp, disp_ref), mu_model
+        if conf:
+            assert np.array_equal(p.batch_mu[0], np.asarray(as_py(res.get("lsMuModel").get("lsmatBatchModel").v[0])))
