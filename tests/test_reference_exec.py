@@ -519,3 +519,49 @@ def test_warm_start_hooks_of_the_executed_reference(oracle):
         assert np.array_equal(p.mat_mu, mu_ref) and np.array_equal(p.mat_disp, disp_ref), mu_model
         if conf:
             assert np.array_equal(p.batch_mu[0], np.asarray(as_py(res.get("lsMuModel").get("lsmatBatchModel").v[0])))
+
+
+@pytest.mark.skipif(not glob.glob("/root/reference/R/*.R"), reason="the reference's sources exist in the build container only")
+def test_fit_extraction_of_the_executed_reference(oracle):
+    """getFitsMean / getFitsDispersion / getFitsDropout / getPostDrop (calcPostDrop_Matrix) / getNormData with its two
+    switches (getFits.R:52-363, calcPostDrop.R:69-125), executed from the reference's text on a model the reference's
+    fitModel has just fitted -- groups mean and spline dispersion, a batch confounder on each, logistic_ofMu drop-out, size
+    factors -- against the oracle's expansions, which are what the GPU's lpb200_expand_fits is compared with
+    (test_gpu_parity.py::test_fit_extraction_parity, test_post_drop_parity): equal to the last bit, the quirk that the
+    posterior ignores size factors (calcPostDrop.R:110) included."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_exec_golden as gen
+    ref = gen.Reference("/root/reference", dnbinom=lambda x, s, mu: oracle.dnbinom_mu_log(x, s, mu))
+    ref.I.lm_solver = gen.lm_in_the_oracle_s_order
+    d = gen.make_data(12, size_factors=True)
+    G, N = d["counts"].shape
+    t = np.asarray(d["t"], dtype=np.float64)
+    X = np.ascontiguousarray(d["counts"], dtype=np.int32)
+    mat = gen.r_inputs(d)[0]
+    res, out = gen.fit_model(ref, d, strMuModel="groups", strDispModel="splines", strDropModel="logistic_ofMu", scaDFSplinesDisp=3,
+                             vecConfoundersMu=["batch"], vecConfoundersDisp=["batch"], cycles=2)
+    mu, disp, drop = res.get("lsMuModel"), res.get("lsDispModel"), res.get("lsDropModel")
+    design = A.DesignData(G, N, size_factors=np.asarray(d["sf"], dtype=np.float64), pseudotime=t, groups=d["groups"],
+                          spline_basis_disp=ns(t, 3), impulse_basis=ns(t, 4), confounders_mu=[d["batch"]], confounders_disp=[d["batch"]])
+    m = model("groups", "splines", "logistic_ofMu")
+    p = A.ParamsData(design, m)
+    p.mat_mu = np.asfortranarray(np.asarray(out["matMuModel"], dtype=np.float64).reshape(p.mat_mu.shape))
+    p.mat_disp = np.asfortranarray(np.asarray(out["matDispModel"], dtype=np.float64).reshape(p.mat_disp.shape))
+    p.batch_mu = [np.asfortranarray(np.asarray(out["lsmatBatchModelMu"][0], dtype=np.float64))]
+    p.batch_disp = [np.asfortranarray(np.asarray(out["lsmatBatchModelDisp"][0], dtype=np.float64))]
+    p.mat_drop = np.asfortranarray(np.asarray(out["matDropoutLinModel"], dtype=np.float64).reshape(p.mat_drop.shape))
+    ids, gi = gen.S(["gene_2", "gene_7", "gene_1"]), [1, 6, 0]
+    got = {"getFitsMean": (ref.call("getFitsMean", lsMuModel=mu, vecGeneIDs=ids), A.EXPAND_MEAN),
+           "getFitsDispersion": (ref.call("getFitsDispersion", lsDispModel=disp, vecGeneIDs=ids), A.EXPAND_DISP),
+           "getFitsDropout": (ref.call("getFitsDropout", lsMuModel=mu, lsDropModel=drop, vecGeneIDs=ids), A.EXPAND_DROP),
+           "getNormData": (ref.call("getNormData", matCounts=mat, lsMuModel=mu, vecGeneIDs=ids), A.EXPAND_NORMDATA),
+           "getNormData(boolDepth = FALSE)": (ref.call("getNormData", matCounts=mat, lsMuModel=mu, vecGeneIDs=ids, boolDepth=gen.B(False)),
+                                              A.EXPAND_NORMDATA | A.EXPAND_NO_DEPTH),
+           "getNormData(boolBatch = FALSE)": (ref.call("getNormData", matCounts=mat, lsMuModel=mu, vecGeneIDs=ids, boolBatch=gen.B(False)),
+                                              A.EXPAND_NORMDATA | A.EXPAND_NO_BATCH)}
+    for name, (r, what) in got.items():
+        assert r.dim == (3, N), name
+        assert np.array_equal(oracle.expand_fits(X, design, m, p, gi, what), r.mat()), name
+    r = ref.call("getPostDrop", matCounts=mat, lsMuModel=mu, lsDispModel=disp, lsDropModel=drop, vecGeneIDs=ids)
+    assert np.array_equal(oracle.post_drop(X, design, m, p, gi), r.mat())
