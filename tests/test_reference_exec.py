@@ -565,3 +565,38 @@ def test_fit_extraction_of_the_executed_reference(oracle):
         assert np.array_equal(oracle.expand_fits(X, design, m, p, gi, what), r.mat()), name
     r = ref.call("getPostDrop", matCounts=mat, lsMuModel=mu, lsDispModel=disp, lsDropModel=drop, vecGeneIDs=ids)
     assert np.array_equal(oracle.post_drop(X, design, m, p, gi), r.mat())
+
+
+@pytest.mark.skipif(not glob.glob("/root/reference/R/*.R"), reason="the reference's sources exist in the build container only")
+def test_test_dropout_of_the_executed_reference(oracle):
+    """testDropout (runHypothesisTests.R:179-214) executed from the reference's text on the object its own runLineagePulse
+    returned, against the product's testDropout on the same results table and drop-out model: every column equal to the last
+    bit for the per-cell drop-out model, and for "ForAllCells" the reference's quirk -- it tests for "AllCells", so no
+    drop-out parameter is counted, the difference in degrees of freedom is 0 and the p-value 0."""
+    import sys
+    import pandas as pd
+    import lineagepulse_b200 as lp
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_reference_exec_golden as gen
+    from tests.r_eval import as_py
+    ref = gen.Reference("/root/reference", dnbinom=lambda x, s, mu: oracle.dnbinom_mu_log(x, s, mu))
+    ref.I.lm_solver = gen.lm_in_the_oracle_s_order
+    d = gen.make_data(21, G=8, N=24, size_factors=True)
+    mat, df, sf = gen.r_inputs(d)
+    df.attrs = {"class": "data.frame", "row.names": list(df.v[0].v)}
+    for grp in ("PerCell", "ForAllCells"):
+        obj = ref.call("runLineagePulse", counts=mat, dfAnnotation=df, boolVerbose=gen.B(False), strMuModel=gen.S("groups"),
+                       strDropModel=gen.S("logistic"), strDropFitGroup=gen.S(grp), vecNormConstExternal=sf)
+        want = ref.call("testDropout", objLP=obj)
+        slot = lambda name: obj.v[obj.names.index(name)]     # noqa: E731
+        res, drop = slot("dfResults"), slot("lsDropModel")
+        table = pd.DataFrame({n: [np.nan if x is None else x for x in as_py(c)] for n, c in zip(res.names, res.v)
+                              if n not in ("gene", "allZero")})
+        mine = lp.LineagePulseObject(dfResults=table, lsDropModel={
+            "matDropoutLinModel": np.asarray(as_py(drop.get("matDropoutLinModel")), dtype=np.float64),
+            "lsDropModelGlobal": {"strDropFitGroup": drop.get("lsDropModelGlobal").get("strDropFitGroup").v[0]}})
+        got = lp.testDropout(mine)
+        assert list(got.columns) == want.names
+        for name, col in zip(want.names, want.v):
+            assert got[name].tolist() == as_py(col), (grp, name)
+        assert (got["df_delta"][0] == 0 and got["p"][0] == 0.0) == (grp == "ForAllCells")
