@@ -539,8 +539,11 @@ def test_fit_extraction_of_the_executed_reference(oracle):
     t = np.asarray(d["t"], dtype=np.float64)
     X = np.ascontiguousarray(d["counts"], dtype=np.int32)
     mat = gen.r_inputs(d)[0]
+    # the drop-out model of a constant-mean EM (seconds), then the rich model given it (the per-cell fits are the slow part of
+    # the evaluator)
+    drop_a = gen.fit_model(ref, d, strMuModel="constant", strDispModel="constant", strDropModel="logistic_ofMu")[0].get("lsDropModel")
     res, out = gen.fit_model(ref, d, strMuModel="groups", strDispModel="splines", strDropModel="logistic_ofMu", scaDFSplinesDisp=3,
-                             vecConfoundersMu=["batch"], vecConfoundersDisp=["batch"], cycles=2)
+                             vecConfoundersMu=["batch"], vecConfoundersDisp=["batch"], lsDropModel=drop_a)
     mu, disp, drop = res.get("lsMuModel"), res.get("lsDispModel"), res.get("lsDropModel")
     design = A.DesignData(G, N, size_factors=np.asarray(d["sf"], dtype=np.float64), pseudotime=t, groups=d["groups"],
                           spline_basis_disp=ns(t, 3), impulse_basis=ns(t, 4), confounders_mu=[d["batch"]], confounders_disp=[d["batch"]])
